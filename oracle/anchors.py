@@ -1,0 +1,138 @@
+"""Independent anchors for the oracle, and the host-CPU reference arm.
+
+TEST INFRASTRUCTURE ONLY (same import rules as ``oracle/__init__.py``).
+
+The reference's arithmetic lives in Caffe and OpenCV-contrib ``ximgproc``; neither is in
+this image and neither can be installed offline.  What *is* here and is
+third-party code reading the reference's real artefacts / implementing the same
+algorithm:
+
+* ``cv2.dnn.readNetFromCaffe(prototxt, caffemodel)`` -- OpenCV's own Caffe importer and
+  CPU inference (anchor for decompose_with_trained_CNN.py:82-95).
+* ``cv2.bilateralFilter(img, -1, sc, ss)`` -- same algorithm as
+  ``jointBilateralFilter_8u`` when joint == src (anchor for filter_reflectance.py:60-64).
+* ``cv2.boxFilter(..., normalize=True, borderType=BORDER_REFLECT)`` -- the primitive
+  ``ximgproc::guidedFilter`` is built on (filter_reflectance.py:67-70).
+
+These are also what ``bench.py --impl reference`` times.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+try:  # cv2 is part of the image; keep the import error readable if it is not
+    import cv2
+except Exception as e:  # pragma: no cover
+    cv2 = None
+    _cv2_err = e
+
+
+def _need_cv2():
+    if cv2 is None:
+        raise RuntimeError("cv2 is required for the oracle anchors: %r" % (_cv2_err,))
+
+
+def input_blob_reference(image_bgr_u8: np.ndarray) -> np.ndarray:
+    """decompose_with_trained_CNN.py:57-69 restated with numpy float64, cast to float32 as
+    the assignment into the Caffe blob does (:88)."""
+    blob = image_bgr_u8 / 255.0
+    blob = blob[:, :, ::-1]
+    lin = np.where(blob <= 0.04045, blob / 12.92, np.power((blob + 0.055) / 1.055, 2.4))
+    return np.ascontiguousarray(np.transpose(lin, (2, 0, 1))[np.newaxis].astype(np.float32))
+
+
+class DnnNet:
+    """cv2.dnn-backed stand-in for ``caffe.Net(prototxt, caffe.TEST, weights=caffemodel)``."""
+
+    def __init__(self, prototxt: str, caffemodel: str):
+        _need_cv2()
+        self.net = cv2.dnn.readNetFromCaffe(prototxt, caffemodel)
+
+    def forward(self, image_bgr_u8: np.ndarray) -> np.ndarray:
+        self.net.setInput(input_blob_reference(image_bgr_u8))
+        out = self.net.forward()
+        assert out.shape[0] == 1 and out.shape[1] == 1
+        return out[0, 0].copy()
+
+    def layer_params(self):
+        """``{layer: (W, b)}`` as cv2.dnn parsed them (independent of our wire reader)."""
+        out = {}
+        for name in self.net.getLayerNames():
+            lid = self.net.getLayerId(name)
+            try:
+                w = self.net.getParam(lid, 0)
+                b = self.net.getParam(lid, 1)
+            except cv2.error:
+                continue
+            if w is not None and w.size:
+                out[name] = (np.asarray(w), np.asarray(b))
+        return out
+
+
+def bilateral_self(image_u8: np.ndarray, sigma_color: float, sigma_space: float) -> np.ndarray:
+    """cv2.bilateralFilter(d=-1): equals jointBilateralFilter(joint=src copy)."""
+    _need_cv2()
+    return cv2.bilateralFilter(image_u8, -1, float(sigma_color), float(sigma_space))
+
+
+def box_mean_cv2(plane_f32: np.ndarray, r: int) -> np.ndarray:
+    _need_cv2()
+    k = 2 * int(r) + 1
+    return cv2.boxFilter(plane_f32, cv2.CV_32F, (k, k), normalize=True, borderType=cv2.BORDER_REFLECT)
+
+
+def guided_cv2box(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: float) -> np.ndarray:
+    """SURVEY A.3 written on cv2.boxFilter with float32 pointwise arithmetic."""
+    _need_cv2()
+    f32 = np.float32
+    eps = f32(eps)
+    I = [guide_u8[:, :, c].astype(f32) for c in range(3)]
+    src = src_u8 if src_u8.ndim == 3 else src_u8[:, :, None]
+    mean = lambda x: box_mean_cv2(x, radius)
+    mI = [mean(x) for x in I]
+    cov = {}
+    for k in range(3):
+        for l in range(k, 3):
+            v = mean(I[k] * I[l]) - mI[k] * mI[l]
+            if k == l:
+                v = v + eps
+            cov[(k, l)] = cov[(l, k)] = v
+    cof = {}
+    for k in range(3):
+        for l in range(k, 3):
+            k1, k2, l1, l2 = (k + 1) % 3, (k + 2) % 3, (l + 1) % 3, (l + 2) % 3
+            cof[(k, l)] = cof[(l, k)] = cov[(k1, l1)] * cov[(k2, l2)] - cov[(k1, l2)] * cov[(k2, l1)]
+    det = cov[(0, 0)] * cof[(0, 0)]
+    det = det + cov[(0, 1)] * cof[(0, 1)]
+    det = det + cov[(0, 2)] * cof[(0, 2)]
+    if eps < 1e-2:
+        det = np.where(np.abs(det) < 1e-6, f32(1e-6), det)
+    inv = {key: v / det for key, v in cof.items()}
+    out = np.empty(src.shape, np.uint8)
+    for si in range(src.shape[2]):
+        p = src[:, :, si].astype(f32)
+        mp = mean(p)
+        c = [mean(p * I[g]) - mp * mI[g] for g in range(3)]
+        al = []
+        for g in range(3):
+            v = inv[(g, 0)] * c[0]
+            v = v + inv[(g, 1)] * c[1]
+            v = v + inv[(g, 2)] * c[2]
+            al.append(v)
+        be = mp
+        for g in range(3):
+            be = be - al[g] * mI[g]
+        mb = mean(be)
+        ma = [mean(a) for a in al]
+        q = mb
+        for g in range(3):
+            q = q + ma[g] * I[g]
+        out[:, :, si] = np.clip(np.rint(q), 0, 255).astype(np.uint8)
+    return out if src_u8.ndim == 3 else out[:, :, 0]
+
+
+def quantize_like_imwrite(gray_f32: np.ndarray) -> np.ndarray:
+    """image_utils.py:60-73 for the CNN output: normalize is a no-op (sigmoid < 1), then
+    ``(image * 255).astype(np.uint8)``; cv2.imread of the 1-channel PNG replicates it to
+    three equal channels."""
+    return (gray_f32 * 255).astype(np.uint8)
