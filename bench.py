@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the CNN -> joint bilateral filter hot path (BASELINE.json metric: megapixels/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [--steps K] [--warmup W]      # host-CPU reference-equivalent path
+
+Workload (BASELINE.json configs[1]): synthetic 512x384 sRGB images -> CNN reflectance ->
+trunc(r*255) -> BF(CNN, CNN) c20 s22.  One step = one batch of `--batch` such images per GPU
+(weak scaling: every rank processes its own shard of the batch, no communication on the pixel
+path).  Inputs rotate through a pool larger than L2 so no step re-reads cached inputs.
+
+`value`   : device-resident uint8 in -> uint8 out, CUDA-event time over exactly K steps, max over ranks.
+`e2e`     : the same steps through Pipeline.run_host: pinned HOST buffers in, HOST buffers out, H2D
+            and D2H copies inside the timed region.
+`roofline`: the dominant kernel (bf_gray_kernel), timed per launch with CUDA events in a second pass
+            over the same steps.
+`cpu_baseline`: the reference-equivalent CPU path (cv2.dnn on the real prototxt/caffemodel +
+            cv2.bilateralFilter, bit-identical to the restated jointBilateralFilter_8u) on a
+            bounded sample, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 384, 512
+SIGMA_COLOR, SIGMA_SPATIAL = 20.0, 22.0
+CONFIG_ID = 2
+METRIC = "megapixels/sec end-to-end CNN->BF(CNN,CNN) c20 s22 (device-resident uint8 in -> uint8 out)"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clock sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-equivalent CPU path (also the --impl reference arm)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step(images, dnn):
+    """One image at a time, as the reference CLI chain does: CNN (cv2.dnn on the real artefacts,
+    reference input transform), trunc(r*255), replicate to 3 channels (cv2.imread of the gray PNG),
+    bilateral c20 s22 with a copy of itself as joint (== cv2.bilateralFilter)."""
+    from oracle import anchors
+    outs = []
+    for img in images:
+        r = dnn.forward(img)
+        g3 = np.repeat(anchors.quantize_like_imwrite(r)[:, :, None], 3, axis=2)
+        outs.append(anchors.bilateral_self(g3, SIGMA_COLOR, SIGMA_SPATIAL))
+    return outs
+
+
+def time_cpu(n_images: int, steps: int, warmup: int):
+    import cv2
+    from oracle import anchors
+    from reflectance_filtering_b200 import synth
+    from reflectance_filtering_b200.caffe_model import DEFAULT_CAFFEMODEL, DEFAULT_PROTOTXT
+    cores = os.cpu_count() or 1
+    cv2.setNumThreads(cores)
+    dnn = anchors.DnnNet(DEFAULT_PROTOTXT, DEFAULT_CAFFEMODEL)
+    imgs = [synth.natural(H, W, 1000 * CONFIG_ID + i) for i in range(n_images)]
+    for _ in range(warmup):
+        cpu_reference_step(imgs[:1], dnn)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(imgs, dnn)
+    dt = time.perf_counter() - t0
+    mp = steps * n_images * H * W / 1e6
+    return mp / dt, dt / steps, cores, cv2.getNumThreads()
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    n_img = 1
+    mps, s_per_step, cores, cvt = time_cpu(n_img, args.steps, min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mps, "unit": "MP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 weights/sums, u8 pixels", "data": "synthetic",
+        "config": {"workload": "configs[1]: 512x384 CNN -> BF(CNN,CNN) c20 s22", "images_per_step": n_img,
+                   "height": H, "width": W, "sigma_color": SIGMA_COLOR, "sigma_spatial": SIGMA_SPATIAL},
+        "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
+                         "sample": "%d step(s) x %d image(s) of 512x384: cv2.dnn forward on the reference "
+                                   "prototxt+caffemodel, trunc, cv2.bilateralFilter c20 s22; cv2 threads=%d"
+                                   % (args.steps, n_img, cvt)},
+        "e2e": {"value": mps, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------
+def run_cuda(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    from reflectance_filtering_b200 import _native, cnn, filters, pipeline, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+
+    B = args.batch
+    net = cnn.default_net(device)
+    pipe = pipeline.Pipeline(net)
+
+    # ---- synthetic pool, larger than L2, built from per-image seeded generators ------------------
+    n_distinct = min(B, 32)
+    lo = rank * B  # every rank draws its own shard of the (world * B)-image batch
+    base = np.stack([synth.natural(H, W, 1000 * CONFIG_ID + lo + i) for i in range(n_distinct)])
+    batch_bytes = B * H * W * 3
+    n_pool = max(2, int(np.ceil(2.0 * L2_BYTES / batch_bytes)))
+    host_pool = torch.empty((n_pool, B, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    for p in range(n_pool):
+        for i in range(B):
+            src = base[(i + p) % n_distinct]
+            host_pool[p, i] = torch.from_numpy(np.roll(src, shift=(7 * p + 3 * (i // n_distinct)) % W, axis=1))
+    dev_pool = host_pool.to(device)
+    out_pool = torch.empty((n_pool, B, H, W), dtype=torch.uint8, device=device)
+    host_out = torch.empty((n_pool, B, H, W), dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def step(i):
+        p = i % n_pool
+        pipe.cnn_bf(dev_pool[p], SIGMA_COLOR, SIGMA_SPATIAL, out=out_pool[p])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    launches = _native.launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    px_step = B * H * W
+    value = world * px_step * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- end to end through host buffers ----------------------------------------------------------
+    def e2e_step(i):
+        p = i % n_pool
+        pipe.run_host("cnn_bf", host_pool[p], host_out[p], chunk=args.chunk, n_streams=3,
+                      sigma_color=SIGMA_COLOR, sigma_spatial=SIGMA_SPATIAL)
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(args.warmup + i)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+    e2e_value = world * px_step * args.steps / (e2e_ms * 1e-3) / 1e6
+    e2e_ok = bool(torch.equal(host_out[(args.warmup + args.steps - 1) % n_pool].to(device),
+                              out_pool[(args.warmup + args.steps - 1) % n_pool]))
+
+    # ---- per-kernel pass: the same steps with events around each launch ------------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        p = (args.warmup + i) % n_pool
+        ev[i][0].record()
+        r8 = pipe.reflectance_u8(dev_pool[p])
+        ev[i][1].record()
+        filters.joint_bilateral_device(r8, r8, SIGMA_COLOR, SIGMA_SPATIAL, d=-1, gray_replicated=True,
+                                       out=out_pool[p])
+        ev[i][2].record()
+    barrier()
+    cnn_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    bf_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    import ctypes as C
+    r_, t_ = C.c_int(), C.c_int()
+    _native.lib().rf_joint_bilateral_geometry(SIGMA_SPATIAL, -1, C.byref(r_), C.byref(t_))
+    taps = t_.value
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    f_max = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    f_obs = (clocks.get("sm_mhz") or 0) * 1e6
+    taps_per_launch = float(px_step) * taps
+    # gray fast path: 4 FP32 lane-ops + 1 exp per tap; MUFU.EX2 issues 16 lanes/clk/SM
+    sfu_peak = sms * 16 * f_max
+    alu_peak = sms * 128 * f_max
+    achieved_taps = taps_per_launch / (bf_ms * 1e-3)
+    roofline = {
+        "kernel": "bf_gray_kernel", "bound": "sfu", "achieved": achieved_taps / 1e9, "peak": sfu_peak / 1e9,
+        "unit": "Gtap/s (1 MUFU.EX2 per tap; peak = SMs*16*sm_max_mhz)", "frac": achieved_taps / sfu_peak,
+        "frac_at_observed_clock": (achieved_taps / (sms * 16 * f_obs)) if f_obs else None,
+        "fp32_lane_ops": {"per_tap": 4, "achieved_Gop_s": achieved_taps * 4 / 1e9, "peak_Gop_s": alu_peak / 1e9,
+                          "frac": achieved_taps * 4 / alu_peak},
+        "taps_per_pixel": taps, "launch_ms": bf_ms, "share_of_step": bf_ms / (bf_ms + cnn_ms),
+        "traffic": None, "peak_source": "SM count x unit width x %s clock" % peak_src,
+    }
+    cnn_flops = 8704.0 * px_step
+    cnn_roof = {"kernel": "mlp_kernel<32>", "bound": "fp32 cuda cores", "launch_ms": cnn_ms,
+                "achieved_tflops": cnn_flops / (cnn_ms * 1e-3) / 1e12, "peak_tflops": alu_peak * 2 / 1e12,
+                "frac": cnn_flops / (cnn_ms * 1e-3) / (alu_peak * 2),
+                "vs_bf16_tensor_peak": cnn_flops / (cnn_ms * 1e-3) / 1e12 / float(peaks.get("bf16_tflops", 1590.0))}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        mps, s_per, cores, cvt = time_cpu(args.cpu_images, 1, 1)
+        cpu = {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
+               "sample": "%d image(s) of 512x384 through cv2.dnn (reference prototxt+caffemodel) + trunc + "
+                         "cv2.bilateralFilter c20 s22, cv2 threads=%d, %.1f s" % (args.cpu_images, cvt, s_per)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 weights/sums, u8 pixels", "data": "synthetic",
+        "config": {"workload": "configs[1]: 512x384 CNN -> trunc u8 -> BF(CNN,CNN) c20 s22 (r=33, %d taps/px)" % taps,
+                   "images_per_step_per_gpu": B, "height": H, "width": W, "sigma_color": SIGMA_COLOR,
+                   "sigma_spatial": SIGMA_SPATIAL, "cache": "inputs rotate through a %d-batch pool (%.0f MB > L2)"
+                   % (n_pool, n_pool * batch_bytes / 1e6), "parallelism": "dp%d, contiguous image shards, no collective" % world},
+        "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": world * batch_bytes,
+                "d2h_bytes_per_step": world * px_step, "ms_per_step": e2e_ms / args.steps,
+                "api": "Pipeline.run_host(pinned host uint8[N,H,W,3] -> pinned host uint8[N,H,W])",
+                "matches_device_path": e2e_ok},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_cnn": cnn_roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per step per GPU")
+    ap.add_argument("--chunk", type=int, default=16, help="images per H2D/compute/D2H chunk in the e2e path")
+    ap.add_argument("--cpu-images", type=int, default=6, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_cuda(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

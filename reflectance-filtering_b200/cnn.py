@@ -1,0 +1,124 @@
+"""Direct reflectance prediction with the WHDR CNN on the GPU.
+
+Host-side mirror of /root/reference/decompose_with_trained_CNN.py.  :class:`Net` stands where
+``caffe.Net(network_file, caffe.TEST, weights=caffemodel)`` stood (:104-106): it reads the
+*unchanged* ``network_definition.prototxt`` + ``learned_weights.caffemodel`` (blobs matched by
+layer name) and uploads them once per device.  :func:`get_reflectance_caffe` (:82-95) and
+:func:`decompose_image` (:98-130) keep the reference's names, arguments, return types, output
+file names and error behaviour.  The input transform of ``imgCV2_to_caffeBlob`` (:57-69) is
+fused into the kernel as a 256-entry table (``image_utils.srgb_lut``).
+"""
+from __future__ import division, print_function
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _native, caffe_model, device as dev, image_utils as iu
+
+TEST = 1  # caffe.TEST, accepted and ignored (the deploy graph has no phase-dependent layer)
+
+
+class Net(object):
+    """The deploy network, resident on one CUDA device."""
+
+    def __init__(self, network_file=caffe_model.DEFAULT_PROTOTXT, phase=TEST,
+                 weights=caffe_model.DEFAULT_CAFFEMODEL, device=None):
+        self.mlp = caffe_model.build_pixel_mlp(network_file, weights)
+        if self.mlp.concat != list(range(len(self.mlp.hidden))):
+            raise ValueError("the Concat layer must take every hidden map in order; got %r"
+                             % (self.mlp.concat,))
+        self.device = dev.bind_device(device)
+        params = self.mlp.flat_params()
+        dims = np.asarray(self.mlp.dims(), np.int32)
+        lut = np.ascontiguousarray(iu.srgb_lut(), np.float32)
+        handle = C.c_void_p()
+        _native.check(_native.lib().rf_cnn_create(
+            params.ctypes.data_as(C.c_void_p), dims.ctypes.data_as(C.c_void_p), len(dims) - 1,
+            lut.ctypes.data_as(C.c_void_p), C.byref(handle)))
+        self._handle = handle
+        self.inputs = [self.mlp.input_blob]
+        self.outputs = [self.mlp.output_blob]
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _native.lib().rf_cnn_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def forward_device(self, images: torch.Tensor, want_f32: bool = True, want_u8: bool = False):
+        """``uint8[N,H,W,3]`` BGR CUDA tensor -> (``float32[N,H,W]`` linear reflectance intensity
+        or None, ``uint8[N,H,W]`` = trunc(r * 255) or None); asynchronous on the current stream."""
+        dev.check_u8_cuda(images, "images")
+        if images.dim() != 4 or images.shape[3] != 3:
+            raise ValueError("images must be [N,H,W,3], got %r" % (tuple(images.shape),))
+        if images.device != self.device:
+            raise ValueError("images live on %s, the network on %s" % (images.device, self.device))
+        n, h, w, _ = images.shape
+        f32 = torch.empty((n, h, w), dtype=torch.float32, device=self.device) if want_f32 else None
+        u8 = torch.empty((n, h, w), dtype=torch.uint8, device=self.device) if want_u8 else None
+        with torch.cuda.device(self.device):
+            dev.bind_device(self.device)
+            _native.check(_native.lib().rf_cnn_forward_u8(
+                self._handle, dev.ptr(images), n, h, w,
+                dev.ptr(f32) if want_f32 else C.c_void_p(0),
+                dev.ptr(u8) if want_u8 else C.c_void_p(0), dev.stream_ptr()))
+        return f32, u8
+
+
+_default_nets = {}
+
+
+def default_net(device=None) -> Net:
+    """The shipped model, built once per device (the reference rebuilds caffe.Net per call)."""
+    d = dev.bind_device(device)
+    net = _default_nets.get(d.index)
+    if net is None:
+        net = _default_nets[d.index] = Net(device=d)
+    return net
+
+
+def caffeBlob_to_imgGrayLinear(blob):
+    """Take a [1,1,H,W] blob and turn it into an H x W image (decompose...py:72-79)."""
+    b, c = blob.shape[:2]
+    if b != 1 or c != 1:
+        raise ValueError("Expecting to get 1 image in mini-batch having 1 channel, "
+                         "but got batch size of {} and {} channels".format(b, c))
+    return blob[0, 0, :, :]
+
+
+def get_reflectance_caffe(net, image):
+    """Run the image through the network and return the result (decompose...py:82-95):
+    ``uint8[H,W,3]`` BGR -> ``float32[H,W]`` linear reflectance intensity."""
+    if not isinstance(image, np.ndarray) or image.dtype != np.uint8 or image.ndim != 3 \
+            or image.shape[2] != 3:
+        raise ValueError("image must be a uint8 H x W x 3 BGR array as cv2.imread returns it")
+    dev.bind_device(net.device)
+    t = dev.to_device(image, "cnn_in")[None]
+    f32, _ = net.forward_device(t, want_f32=True, want_u8=False)
+    blob = dev.to_host(f32, "cnn_out")[:, None, :, :]
+    return caffeBlob_to_imgGrayLinear(blob)
+
+
+get_reflectance = get_reflectance_caffe
+
+
+def decompose_image(filename_in, path_out, net=None):
+    """Run the intrinsic image decomposition (decompose...py:98-130): writes ``<base>-r.png``
+    (linear gray), ``<base>-r_colorized.png`` and ``<base>-s_colorized.png`` (sRGB) into
+    ``path_out`` and returns the float32 reflectance intensity."""
+    if net is None:
+        net = default_net()
+    image = iu.imread(filename_in)
+    stem = os.path.splitext(os.path.basename(filename_in))[0]
+    reflectance_gray = get_reflectance_caffe(net, image)
+    iu.imwrite(os.path.join(path_out, stem + '-r.png'), reflectance_gray)
+    reflectance, shading = iu.colorize(reflectance_gray, image)
+    iu.imwrite(os.path.join(path_out, stem + '-r_colorized.png'), reflectance, sRGB=True)
+    iu.imwrite(os.path.join(path_out, stem + '-s_colorized.png'), shading, sRGB=True)
+    return reflectance_gray

@@ -1,0 +1,367 @@
+// Guided filter (colour guide, 8-bit) for sm_100a.
+//
+// Replaces cv2.ximgproc.guidedFilter(guide, src, radius, eps) at
+// /root/reference/filter_reflectance.py:67-70 (semantics: OpenCV-contrib 3.1.0 guided_filter.cpp,
+// SURVEY.md Appendix A.3): 33 normalised (2r+1)^2 box means with BORDER_REFLECT, cov(I) + eps*Id on
+// the 0..255 scale, per-pixel 3x3 inverse by cofactors, q = mean(a).I + mean(b), round-half-even.
+//
+// Two streaming passes (DESIGN.md "K4"):
+//   pass A  reads guide + src (u8), forms the 9 + 4*SC window sums I, I*I', p, p*I as EXACT uint32
+//           integers (products <= 65,025, window <= 481^2 => < 2^32), converts each to the box
+//           mean exactly as OpenCV does -- float(double(sum) * (1.0 / (2r+1)^2)) -- and solves
+//           for (a0, a1, a2, b) per source channel; writes one float4 per pixel per channel.
+//   pass B  box-means the four coefficient planes with FP64 running sums (OpenCV's box filter
+//           accumulates CV_32F input in double), applies q = b + a.I and writes uint8.
+// Both passes give every thread one image column of a vertical strip: the vertical window sum
+// lives in registers and slides down the strip (add the entering row, subtract the leaving
+// one); the horizontal window sum is a block-wide prefix scan (warp shuffles + one shared-memory
+// hop) followed by P[x+r] - P[x-r-1].  All elementwise FP32 math uses the non-contracting
+// __fmul_rn/__fadd_rn forms so pass A reproduces the oracle's separate multiply/add bit for bit.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace rf {
+namespace gf {
+
+constexpr int NT = 512;      // threads per CTA = columns per strip including the 2r halo
+constexpr int NW = NT / 32;  // warps
+constexpr int MAX_RADIUS = (NT - 32) / 2;
+
+struct Args {
+    const uint8_t *guide;  // [n][h][w][3]
+    const uint8_t *src;    // [n][h][w][SC]
+    float4 *ab;            // [n][SC][h][w] (a0, a1, a2, b)
+    uint8_t *dst;          // [n][h][w][SC]
+    int n, h, w, r;
+    int twa;       // output columns per strip
+    int seg_rows;  // output rows per CTA
+    float eps;
+    double scale;  // 1 / (2r+1)^2
+};
+
+// ---- block-wide inclusive scan of Q per-thread values, result left in v[] -----------------------
+// pref[q][0] must be zero; on return pref[q][tid + 1] holds the inclusive prefix of column tid.
+template <typename T, int Q>
+__device__ __forceinline__ void block_scan_to_smem(T (&v)[Q], T *pref, T *wtot)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        T x = v[q];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const T t = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += t;
+        }
+        v[q] = x;
+        if (lane == 31) wtot[q * NW + warp] = x;
+    }
+    __syncthreads();
+    if (warp < (Q * NW + 31) / 32) {
+        const bool live = tid < Q * NW;
+        const T own = live ? wtot[tid] : T(0);
+        T inc = own;
+#pragma unroll
+        for (int d = 1; d < NW; d <<= 1) {
+            const T t = __shfl_up_sync(0xffffffffu, inc, d, NW);
+            if ((tid & (NW - 1)) >= d) inc += t;
+        }
+        if (live) wtot[tid] = inc - own;  // exclusive offset of each warp
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        v[q] += wtot[q * NW + warp];
+        pref[q * (NT + 1) + tid + 1] = v[q];
+    }
+    __syncthreads();
+}
+
+// ---- pass A --------------------------------------------------------------------------------------
+template <int SC>
+struct PixA {
+    uint32_t f[9 + 4 * SC];
+    __device__ __forceinline__ void load(const uint8_t *g, const uint8_t *s)
+    {
+        const uint32_t i0 = g[0], i1 = g[1], i2 = g[2];
+        f[0] = i0; f[1] = i1; f[2] = i2;
+        f[3] = i0 * i0; f[4] = i0 * i1; f[5] = i0 * i2;
+        f[6] = i1 * i1; f[7] = i1 * i2; f[8] = i2 * i2;
+#pragma unroll
+        for (int c = 0; c < SC; ++c) {
+            const uint32_t p = s[c];
+            f[9 + 4 * c] = p;
+            f[10 + 4 * c] = p * i0;
+            f[11 + 4 * c] = p * i1;
+            f[12 + 4 * c] = p * i2;
+        }
+    }
+};
+
+template <int SC>
+__global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
+{
+    constexpr int Q = 9 + 4 * SC;
+    extern __shared__ __align__(16) uint32_t sm_u32[];
+    uint32_t *pref = sm_u32;              // [Q][NT + 1]
+    uint32_t *wtot = pref + Q * (NT + 1); // [Q][NW]
+    const int tid = threadIdx.x;
+    const int img = blockIdx.z;
+    const int sx0 = blockIdx.x * g.twa;
+    const int y0 = blockIdx.y * g.seg_rows;
+    const int y1 = min(g.h, y0 + g.seg_rows);
+    const int r = g.r;
+    const int col = sx0 - r + tid;
+    const bool col_active = tid < g.twa + 2 * r;
+    const int xin = reflect(col, g.w);
+    const bool is_out = tid >= r && tid < r + g.twa && col < g.w;
+    const size_t img_px = (size_t)g.h * g.w;
+    const uint8_t *G = g.guide + img * img_px * 3 + (size_t)xin * 3;
+    const uint8_t *S = g.src + img * img_px * SC + (size_t)xin * SC;
+
+    for (int q = tid; q < Q; q += NT) pref[q * (NT + 1)] = 0u;
+
+    uint32_t V[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) V[q] = 0u;
+    if (col_active) {
+        for (int dy = -r; dy < r; ++dy) {
+            const size_t yy = (size_t)reflect(y0 + dy, g.h);
+            PixA<SC> px;
+            px.load(G + yy * g.w * 3, S + yy * g.w * SC);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) V[q] += px.f[q];
+        }
+    }
+    for (int y = y0; y < y1; ++y) {
+        if (col_active) {
+            const size_t yy = (size_t)reflect(y + r, g.h);
+            PixA<SC> px;
+            px.load(G + yy * g.w * 3, S + yy * g.w * SC);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) V[q] += px.f[q];
+        }
+        uint32_t Pq[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) Pq[q] = V[q];
+        block_scan_to_smem<uint32_t, Q>(Pq, pref, wtot);
+        if (is_out) {
+            float m[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const uint32_t s = pref[q * (NT + 1) + tid + r + 1] - pref[q * (NT + 1) + tid - r];
+                m[q] = (float)((double)s * g.scale);  // == cv::boxFilter's float(sum * scale)
+            }
+            // cov(I) + eps on the diagonal; symmetric storage 0:(0,0) 1:(0,1) 2:(0,2) 3:(1,1) 4:(1,2) 5:(2,2)
+            float c00 = __fadd_rn(__fsub_rn(m[3], __fmul_rn(m[0], m[0])), g.eps);
+            float c01 = __fsub_rn(m[4], __fmul_rn(m[0], m[1]));
+            float c02 = __fsub_rn(m[5], __fmul_rn(m[0], m[2]));
+            float c11 = __fadd_rn(__fsub_rn(m[6], __fmul_rn(m[1], m[1])), g.eps);
+            float c12 = __fsub_rn(m[7], __fmul_rn(m[1], m[2]));
+            float c22 = __fadd_rn(__fsub_rn(m[8], __fmul_rn(m[2], m[2])), g.eps);
+            // cofactors with cyclic indices: cof[k][l] = c[k+1][l+1]*c[k+2][l+2] - c[k+1][l+2]*c[k+2][l+1]
+            const float f00 = __fsub_rn(__fmul_rn(c11, c22), __fmul_rn(c12, c12));
+            const float f01 = __fsub_rn(__fmul_rn(c12, c02), __fmul_rn(c01, c22));
+            const float f02 = __fsub_rn(__fmul_rn(c01, c12), __fmul_rn(c11, c02));
+            const float f11 = __fsub_rn(__fmul_rn(c22, c00), __fmul_rn(c02, c02));
+            const float f12 = __fsub_rn(__fmul_rn(c02, c01), __fmul_rn(c12, c00));
+            const float f22 = __fsub_rn(__fmul_rn(c00, c11), __fmul_rn(c01, c01));
+            float det = __fmul_rn(c00, f00);
+            det = __fadd_rn(det, __fmul_rn(c01, f01));
+            det = __fadd_rn(det, __fmul_rn(c02, f02));
+            if (g.eps < 1e-2f && fabsf(det) < 1e-6f) det = 1e-6f;
+            const float i00 = __fdiv_rn(f00, det), i01 = __fdiv_rn(f01, det), i02 = __fdiv_rn(f02, det);
+            const float i11 = __fdiv_rn(f11, det), i12 = __fdiv_rn(f12, det), i22 = __fdiv_rn(f22, det);
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                const float mp = m[9 + 4 * c];
+                const float k0 = __fsub_rn(m[10 + 4 * c], __fmul_rn(mp, m[0]));
+                const float k1 = __fsub_rn(m[11 + 4 * c], __fmul_rn(mp, m[1]));
+                const float k2 = __fsub_rn(m[12 + 4 * c], __fmul_rn(mp, m[2]));
+                float a0 = __fmul_rn(i00, k0);
+                a0 = __fadd_rn(a0, __fmul_rn(i01, k1));
+                a0 = __fadd_rn(a0, __fmul_rn(i02, k2));
+                float a1 = __fmul_rn(i01, k0);
+                a1 = __fadd_rn(a1, __fmul_rn(i11, k1));
+                a1 = __fadd_rn(a1, __fmul_rn(i12, k2));
+                float a2 = __fmul_rn(i02, k0);
+                a2 = __fadd_rn(a2, __fmul_rn(i12, k1));
+                a2 = __fadd_rn(a2, __fmul_rn(i22, k2));
+                float b = __fsub_rn(mp, __fmul_rn(a0, m[0]));
+                b = __fsub_rn(b, __fmul_rn(a1, m[1]));
+                b = __fsub_rn(b, __fmul_rn(a2, m[2]));
+                g.ab[((size_t)(img * SC + c) * g.h + y) * g.w + col] = make_float4(a0, a1, a2, b);
+            }
+        }
+        if (col_active) {
+            const size_t yy = (size_t)reflect(y - r, g.h);
+            PixA<SC> px;
+            px.load(G + yy * g.w * 3, S + yy * g.w * SC);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) V[q] -= px.f[q];
+        }
+    }
+}
+
+// ---- pass B --------------------------------------------------------------------------------------
+template <int SC>
+__global__ void __launch_bounds__(NT) gf_pass_b(const Args g)
+{
+    constexpr int Q = 4 * SC;
+    extern __shared__ __align__(16) double sm_f64[];
+    double *pref = sm_f64;               // [Q][NT + 1]
+    double *wtot = pref + Q * (NT + 1);  // [Q][NW]
+    const int tid = threadIdx.x;
+    const int img = blockIdx.z;
+    const int sx0 = blockIdx.x * g.twa;
+    const int y0 = blockIdx.y * g.seg_rows;
+    const int y1 = min(g.h, y0 + g.seg_rows);
+    const int r = g.r;
+    const int col = sx0 - r + tid;
+    const bool col_active = tid < g.twa + 2 * r;
+    const int xin = reflect(col, g.w);
+    const bool is_out = tid >= r && tid < r + g.twa && col < g.w;
+    const size_t img_px = (size_t)g.h * g.w;
+    const float4 *AB = g.ab + (size_t)img * SC * img_px + xin;
+
+    for (int q = tid; q < Q; q += NT) pref[q * (NT + 1)] = 0.0;
+
+    double V[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) V[q] = 0.0;
+    auto add_row = [&](int yy, double sign) {
+#pragma unroll
+        for (int c = 0; c < SC; ++c) {
+            const float4 v = AB[(size_t)c * img_px + (size_t)yy * g.w];
+            V[4 * c + 0] += sign * (double)v.x;
+            V[4 * c + 1] += sign * (double)v.y;
+            V[4 * c + 2] += sign * (double)v.z;
+            V[4 * c + 3] += sign * (double)v.w;
+        }
+    };
+    if (col_active)
+        for (int dy = -r; dy < r; ++dy) add_row(reflect(y0 + dy, g.h), 1.0);
+    for (int y = y0; y < y1; ++y) {
+        if (col_active) add_row(reflect(y + r, g.h), 1.0);
+        double Pq[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) Pq[q] = V[q];
+        block_scan_to_smem<double, Q>(Pq, pref, wtot);
+        if (is_out) {
+            const uint8_t *gp = g.guide + (img * img_px + (size_t)y * g.w + col) * 3;
+            const float i0 = gp[0], i1 = gp[1], i2 = gp[2];
+            uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + col) * SC;
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                float m[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int q = 4 * c + k;
+                    const double s = pref[q * (NT + 1) + tid + r + 1] - pref[q * (NT + 1) + tid - r];
+                    m[k] = (float)(s * g.scale);
+                }
+                float v = m[3];
+                v = __fadd_rn(v, __fmul_rn(m[0], i0));
+                v = __fadd_rn(v, __fmul_rn(m[1], i1));
+                v = __fadd_rn(v, __fmul_rn(m[2], i2));
+                o[c] = sat_u8(v);
+            }
+        }
+        if (col_active) add_row(reflect(y - r, g.h), -1.0);
+    }
+}
+
+static size_t per_image_ws(int sc, int h, int w) { return (size_t)sc * h * w * sizeof(float4); }
+
+template <int SC>
+static int run(Args a, cudaStream_t st)
+{
+    const size_t smem_a = ((size_t)(9 + 4 * SC) * (NT + 1 + NW)) * sizeof(uint32_t);
+    const size_t smem_b = ((size_t)(4 * SC) * (NT + 1 + NW)) * sizeof(double);
+    static bool configured[64] = {};
+    int dev = 0;
+    RF_CUDA_TRY(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_b<SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured[dev & 63] = true;
+    }
+    const int max_twa = NT - 2 * a.r;
+    const int strips = (a.w + max_twa - 1) / max_twa;
+    a.twa = (a.w + strips - 1) / strips;
+    // split rows only when the grid would leave most SMs idle; each segment pays 2r rows of warm-up
+    int segs = 1;
+    const long ctas = (long)strips * a.n;
+    const int sms = sm_count();
+    if (ctas < sms) {
+        segs = (int)((sms + ctas - 1) / ctas);
+        const int max_segs = a.h / (2 * a.r + 1) > 1 ? a.h / (2 * a.r + 1) : 1;
+        if (segs > max_segs) segs = max_segs;
+    }
+    a.seg_rows = (a.h + segs - 1) / segs;
+    dim3 grid(strips, (a.h + a.seg_rows - 1) / a.seg_rows, a.n);
+    gf_pass_a<SC><<<grid, NT, smem_a, st>>>(a);
+    RF_LAUNCH_CHECK("gf_pass_a");
+    gf_pass_b<SC><<<grid, NT, smem_b, st>>>(a);
+    RF_LAUNCH_CHECK("gf_pass_b");
+    return RF_OK;
+}
+
+}  // namespace gf
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" int rf_guided_max_radius(void) { return gf::MAX_RADIUS; }
+
+extern "C" size_t rf_guided_workspace_bytes(int sc, int n, int h, int w, int radius)
+{
+    (void)radius;
+    if (!(sc == 1 || sc == 3) || n < 1 || h < 1 || w < 1) return 0;
+    // the call processes the batch in chunks if given less; never ask for more than 8 GiB
+    const size_t per = gf::per_image_ws(sc, h, w);
+    size_t want = per * (size_t)n;
+    const size_t cap = (size_t)8 << 30;
+    if (want > cap) want = (cap / per > 0 ? cap / per : 1) * per;
+    return want;
+}
+
+extern "C" int rf_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst, int n, int h,
+                            int w, int radius, double eps, void *ws, size_t ws_bytes, void *stream)
+{
+    if (!guide || !src || !dst || !ws) return fail(RF_EINVAL, "rf_guided_u8: NULL pointer");
+    if (gc != 3) return fail(RF_EUNSUPPORTED, "rf_guided_u8: only 3-channel guides are supported (got %d)", gc);
+    if (!(sc == 1 || sc == 3)) return fail(RF_EINVAL, "rf_guided_u8: src channels must be 1 or 3 (got %d)", sc);
+    if (n < 0 || h < 1 || w < 1) return fail(RF_EINVAL, "rf_guided_u8: bad shape n=%d h=%d w=%d", n, h, w);
+    if (radius < 0) return fail(RF_EINVAL, "rf_guided_u8: negative radius");
+    if (radius > gf::MAX_RADIUS)
+        return fail(RF_EUNSUPPORTED, "rf_guided_u8: radius %d exceeds the supported maximum %d", radius, gf::MAX_RADIUS);
+    if (n == 0) return RF_OK;
+    if (dst == src || dst == guide) return fail(RF_EINVAL, "rf_guided_u8: dst must not alias an input");
+    const size_t per = gf::per_image_ws(sc, h, w);
+    if (ws_bytes < per) return fail(RF_EINVAL, "rf_guided_u8: workspace too small (%zu < %zu bytes)", ws_bytes, per);
+    if ((uintptr_t)ws % 16) return fail(RF_EINVAL, "rf_guided_u8: workspace must be 16-byte aligned");
+    const int k = 2 * radius + 1;
+    int chunk = (int)(ws_bytes / per < (size_t)n ? ws_bytes / per : (size_t)n);
+    if (chunk > 65535) chunk = 65535;
+    const size_t img_px = (size_t)h * w;
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        gf::Args a;
+        a.n = n - i0 < chunk ? n - i0 : chunk;
+        a.guide = guide + i0 * img_px * 3;
+        a.src = src + i0 * img_px * sc;
+        a.dst = dst + i0 * img_px * sc;
+        a.ab = (float4 *)ws;
+        a.h = h;
+        a.w = w;
+        a.r = radius;
+        a.eps = (float)eps;
+        a.scale = 1.0 / ((double)k * k);
+        a.twa = 0;
+        a.seg_rows = 0;
+        int rc = sc == 1 ? gf::run<1>(a, (cudaStream_t)stream) : gf::run<3>(a, (cudaStream_t)stream);
+        if (rc != RF_OK) return rc;
+    }
+    return RF_OK;
+}

@@ -1,0 +1,236 @@
+"""Joint bilateral / guided filtering of a reflectance image on the GPU.
+
+Host-side mirror of /root/reference/filter_reflectance.py: :func:`apply_filter` and
+:func:`read_filter_write` keep the reference's names, arguments, validation messages and
+output file naming (filter_reflectance.py:49-96); the two ``cv2.ximgproc`` calls they make
+(:60-64 and :67-70) are replaced by :func:`joint_bilateral_device` and
+:func:`guided_device`, which launch the sm_100a kernels of ``csrc/bf.cu`` / ``csrc/gf.cu``
+through the C ABI.  The ``*_device`` functions are the batched entry points
+(``uint8[N,H,W,C]`` CUDA tensors in, CUDA tensor out, asynchronous on the current stream).
+"""
+from __future__ import division, print_function
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _native, device as dev, image_utils as iu
+
+
+# --------------------------------------------------------------------------
+# batched device entry points
+# --------------------------------------------------------------------------
+def _nhwc(t: torch.Tensor, name: str):
+    dev.check_u8_cuda(t, name)
+    if t.dim() == 3:
+        n, h, w = t.shape
+        c = 1
+    elif t.dim() == 4:
+        n, h, w, c = t.shape
+    else:
+        raise ValueError("%s must be [N,H,W] or [N,H,W,C], got %r" % (name, tuple(t.shape)))
+    if c not in (1, 3):
+        raise ValueError("%s must have 1 or 3 channels, got %d" % (name, c))
+    return n, h, w, c
+
+
+def joint_bilateral_device(joint: torch.Tensor, src: torch.Tensor, sigma_color: float,
+                           sigma_space: float, d: int = -1, gray_replicated: bool = False,
+                           out: torch.Tensor | None = None) -> torch.Tensor:
+    """``cv2.ximgproc.jointBilateralFilter(joint, src, d, sigmaColor, sigmaSpace)`` for a batch.
+
+    ``gray_replicated``: joint and src are 1-channel planes standing for three equal channels
+    (the CNN's gray PNG as cv2.imread returns it); the result is the common channel."""
+    n, h, w, sc = _nhwc(src, "src")
+    nj, hj, wj, jc = _nhwc(joint, "joint")
+    if (nj, hj, wj) != (n, h, w):
+        raise ValueError("joint and src must have the same batch and spatial size, got %r and %r"
+                         % (tuple(joint.shape), tuple(src.shape)))
+    if joint.device != src.device:
+        raise ValueError("joint and src live on different devices")
+    if out is None:
+        out = torch.empty_like(src)
+    else:
+        dev.check_u8_cuda(out, "out")
+        if out.shape != src.shape:
+            raise ValueError("out must have the shape of src")
+    flags = _native.RF_BF_GRAY_REPLICATED if gray_replicated else 0
+    with torch.cuda.device(src.device):
+        dev.bind_device(src.device)
+        _native.check(_native.lib().rf_joint_bilateral_u8(
+            dev.ptr(joint), jc, dev.ptr(src), sc, dev.ptr(out), n, h, w,
+            float(sigma_color), float(sigma_space), int(d), flags, dev.stream_ptr()))
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _ws_cache.pop(key, None)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def guided_device(guide: torch.Tensor, src: torch.Tensor, radius: int, eps: float,
+                  out: torch.Tensor | None = None,
+                  workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """``cv2.ximgproc.guidedFilter(guide, src, radius, eps)`` for a batch (uint8 out, like src).
+    A 1-channel ``src`` is filtered once; that equals every channel of filtering its 3-channel
+    replication."""
+    n, h, w, sc = _nhwc(src, "src")
+    ng, hg, wg, gc = _nhwc(guide, "guide")
+    if (ng, hg, wg) != (n, h, w):
+        raise ValueError("guide and src must have the same batch and spatial size, got %r and %r"
+                         % (tuple(guide.shape), tuple(src.shape)))
+    if out is None:
+        out = torch.empty_like(src)
+    L = _native.lib()
+    with torch.cuda.device(src.device):
+        dev.bind_device(src.device)
+        need = int(L.rf_guided_workspace_bytes(sc, n, h, w, int(radius)))
+        ws = workspace if workspace is not None else _workspace(src.device, max(need, 16))
+        _native.check(L.rf_guided_u8(dev.ptr(guide), gc, dev.ptr(src), sc, dev.ptr(out), n, h, w,
+                                     int(radius), float(eps), dev.ptr(ws), ws.numel() * ws.element_size(),
+                                     dev.stream_ptr()))
+    return out
+
+
+def replicate_gray_device(gray: torch.Tensor) -> torch.Tensor:
+    """``uint8[...]`` -> ``uint8[..., 3]`` with three equal channels."""
+    dev.check_u8_cuda(gray, "gray")
+    out = torch.empty(tuple(gray.shape) + (3,), dtype=torch.uint8, device=gray.device)
+    with torch.cuda.device(gray.device):
+        dev.bind_device(gray.device)
+        _native.check(_native.lib().rf_replicate_gray_u8(dev.ptr(gray), dev.ptr(out), gray.numel(),
+                                                         dev.stream_ptr()))
+    return out
+
+
+def extract_gray_device(bgr: torch.Tensor, flag: torch.Tensor | None = None) -> torch.Tensor:
+    """First channel of ``uint8[...,3]``; ``flag`` (int32 CUDA scalar preset to 1) is cleared if
+    some pixel does not have three equal channels."""
+    dev.check_u8_cuda(bgr, "bgr")
+    if bgr.shape[-1] != 3:
+        raise ValueError("expected a trailing channel dimension of 3")
+    out = torch.empty(bgr.shape[:-1], dtype=torch.uint8, device=bgr.device)
+    with torch.cuda.device(bgr.device):
+        dev.bind_device(bgr.device)
+        _native.check(_native.lib().rf_extract_gray_u8(
+            dev.ptr(bgr), dev.ptr(out), out.numel(),
+            dev.ptr(flag) if flag is not None else C.c_void_p(0), dev.stream_ptr()))
+    return out
+
+
+def _validate(filter_type, sigma_color, sigma_spatial):
+    # same order and messages as filter_reflectance.py:56-57,71-72
+    if sigma_color <= 0 or sigma_spatial <= 0:
+        raise ValueError("Parameters are expected to be positive.")
+    if filter_type not in ('bilateral', 'guided'):
+        raise ValueError("filter_type must be 'bilateral' or 'guided'.")
+
+
+def apply_filter_device(filter_type, image: torch.Tensor, joint: torch.Tensor, sigma_color,
+                        sigma_spatial, gray_replicated: bool = False,
+                        out: torch.Tensor | None = None) -> torch.Tensor:
+    """Batched :func:`apply_filter` on CUDA tensors (same parameter mapping: bilateral uses
+    ``d=-1``; guided uses ``radius=int(sigma_spatial)``, ``eps=sigma_color``)."""
+    _validate(filter_type, sigma_color, sigma_spatial)
+    if filter_type == 'bilateral':
+        return joint_bilateral_device(joint, image, sigma_color, sigma_spatial, d=-1,
+                                      gray_replicated=gray_replicated, out=out)
+    return guided_device(joint, image, int(sigma_spatial), sigma_color, out=out)
+
+
+# --------------------------------------------------------------------------
+# the reference operator surface (numpy in / numpy out)
+# --------------------------------------------------------------------------
+def _as_image(a, name):
+    if not isinstance(a, np.ndarray):
+        raise TypeError("%s must be a numpy array" % name)
+    if a.dtype != np.uint8:
+        # cv2.imread only ever produces uint8 on this path; ximgproc's CV_32F branch
+        # is not reachable from the reference CLI and is not implemented
+        raise TypeError("%s must be uint8 (got %s)" % (name, a.dtype))
+    if a.ndim == 2:
+        a = a[:, :, None]
+    if a.ndim != 3 or a.shape[2] not in (1, 3):
+        raise ValueError("%s must be HxW, HxWx1 or HxWx3, got shape %r" % (name, a.shape))
+    return a
+
+
+def apply_filter(filter_type, image, joint, sigma_color, sigma_spatial):
+    """
+    Apply the joint/guided filter (drop-in for filter_reflectance.py:49-73).
+
+    ``image`` / ``joint``: ``uint8[H,W,3]`` (or 1-channel) numpy arrays as ``iu.imread`` returns
+    them; result: ``uint8`` array shaped like ``image``.  The arrays are copied to the current
+    CUDA device, filtered there and copied back; when both are gray images replicated to three
+    channels (BF(CNN, CNN)) the single-channel kernel is used, which gives identical bytes.
+    """
+    _validate(filter_type, sigma_color, sigma_spatial)
+    squeeze = isinstance(image, np.ndarray) and image.ndim == 2
+    img = _as_image(image, "image")
+    jnt = _as_image(joint, "joint")
+    if img.shape[:2] != jnt.shape[:2]:
+        raise ValueError("image and joint must have the same height and width, got %r and %r"
+                         % (img.shape[:2], jnt.shape[:2]))
+    d = dev.bind_device()
+    same = joint is image
+    timg = dev.to_device(img, "flt_img")[None]
+    tjnt = timg if same else dev.to_device(jnt, "flt_jnt")[None]
+
+    if filter_type == 'guided' and jnt.shape[2] != 3:
+        raise ValueError("guided filter needs a 3-channel guidance image")
+    src_gray = joint_gray = None
+    if img.shape[2] == 3:
+        flag = torch.ones(2, dtype=torch.int32, device=d)
+        src_gray = extract_gray_device(timg, flag[0:1])
+        if filter_type == 'bilateral' and jnt.shape[2] == 3:
+            joint_gray = src_gray if same else extract_gray_device(tjnt, flag[1:2])
+        else:
+            flag[1] = 0
+        f = flag.tolist()  # one small sync: picks the single-channel kernels when legal
+        src_is_gray, joint_is_gray = bool(f[0]), bool(f[1])
+    else:
+        src_is_gray = joint_is_gray = False
+
+    if filter_type == 'bilateral':
+        if src_is_gray and joint_is_gray:
+            g = joint_bilateral_device(joint_gray, src_gray, sigma_color, sigma_spatial, d=-1,
+                                       gray_replicated=True)
+            res = replicate_gray_device(g)
+        else:
+            res = joint_bilateral_device(tjnt, timg, sigma_color, sigma_spatial, d=-1)
+    else:
+        if src_is_gray:
+            g = guided_device(tjnt, src_gray, int(sigma_spatial), sigma_color)
+            res = replicate_gray_device(g)
+        else:
+            res = guided_device(tjnt, timg, int(sigma_spatial), sigma_color)
+    out = dev.to_host(res[0], "flt_out")
+    if squeeze:
+        out = out[:, :, 0]
+    return out
+
+
+def read_filter_write(filter_type,
+                      filename_in, guidance_in,
+                      sigma_color, sigma_spatial,
+                      path_out):
+    """Read input and guidance image, apply filter and write result
+    (filter_reflectance.py:76-96; output name ``<base>_<type>_c<sigma_color>s<sigma_spatial>.png``)."""
+    stem = os.path.splitext(os.path.basename(filename_in))[0]
+    image = iu.imread(filename_in)
+    joint = iu.imread(guidance_in)
+    filtered = apply_filter(filter_type, image, joint, sigma_color, sigma_spatial)
+    suffix = "_{}_c{}s{}".format(filter_type, sigma_color, sigma_spatial)
+    iu.imwrite(os.path.join(path_out, stem + suffix + '.png'), filtered)
+    return filtered

@@ -1,0 +1,266 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, against the committed golden fixtures, and -- at BASELINE.json sizes -- through
+size-independent properties.  Tolerances (BASELINE.json north_star): max abs error <= 1e-3 on the
+linear reflectance; uint8 outputs within +-1 LSB (we additionally bound the fraction of bytes
+that differ at all)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import oracle  # noqa: E402
+from reflectance_filtering_b200 import cnn, filters, image_utils as iu, pipeline, synth  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CNN_TOL = 1e-3          # north_star tolerance on linear reflectance
+CNN_TIGHT = 1e-5        # what exact-FP32 arithmetic actually achieves against the FP32 oracle
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    return np.load(os.path.join(golden_dir, "golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def net():
+    return cnn.default_net()
+
+
+def dev_u8(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def lsb_stats(a, b):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return int(d.max()), float((d != 0).mean())
+
+
+# ---- CNN ---------------------------------------------------------------------------------------
+def test_cnn_known_answers_and_golden(G, net):
+    for bgr, r_ref in zip(G["cnn_solid_bgr"], G["cnn_solid_r"]):
+        r = cnn.get_reflectance_caffe(net, np.tile(bgr, (4, 4, 1)))
+        assert r.dtype == np.float32 and r.shape == (4, 4)
+        assert np.abs(r - r_ref).max() < CNN_TIGHT
+    for key in ("cnn_stress", "cnn_natural"):
+        r = cnn.get_reflectance_caffe(net, G[key + "_in"])
+        assert np.abs(r - G[key + "_r"]).max() < CNN_TIGHT  # cv2.dnn on the real artefacts
+
+
+@pytest.mark.parametrize("h,w,kind", [(384, 512, "natural"), (37, 53, "stress"), (1, 1, "stress"), (3, 1, "stress")])
+def test_cnn_matches_oracle(net, mlp, h, w, kind):
+    img = synth.GENERATORS[kind](h, w, 4242)
+    r = cnn.get_reflectance_caffe(net, img)
+    ref = oracle.mlp_forward(mlp, img)
+    err = np.abs(r - ref).max()
+    assert err < CNN_TOL and err < CNN_TIGHT
+    assert np.abs(r.astype(np.float64) - oracle.mlp_forward_f64(mlp, img)).max() < CNN_TIGHT
+
+
+def test_cnn_fused_quantisation_is_truncation(net, mlp):
+    imgs = synth.batch("natural", 3, 96, 80, 2)
+    f32, u8 = net.forward_device(dev_u8(imgs), want_f32=True, want_u8=True)
+    f32, u8 = f32.cpu().numpy(), u8.cpu().numpy()
+    assert np.array_equal(u8, (f32 * 255).astype(np.uint8))          # image_utils.py:68 on our floats
+    ref = np.stack([oracle.quantize_trunc(oracle.mlp_forward(mlp, im)) for im in imgs])
+    mx, frac = lsb_stats(u8, ref)
+    assert mx <= 1 and frac < 1e-3                                    # only boundary straddlers differ
+    # batch == per-image, odd pixel counts handled
+    odd = synth.batch("stress", 2, 5, 7, 3)
+    a = net.forward_device(dev_u8(odd))[0].cpu().numpy()
+    b = np.stack([cnn.get_reflectance_caffe(net, im) for im in odd])
+    assert np.array_equal(a, b)
+
+
+# ---- joint bilateral ---------------------------------------------------------------------------
+@pytest.mark.parametrize("key,sc,ss", [("bf_c20_s22", 20, 22), ("bf_c15_s28", 15, 28), ("bf_c8_s3", 8, 3)])
+def test_bf_golden_self_guided(G, key, sc, ss):
+    img = G["bf_in"]
+    out = filters.apply_filter("bilateral", img, img.copy(), sc, ss)
+    mx, frac = lsb_stats(out, G[key])                                # cv2.bilateralFilter bytes
+    assert out.shape == img.shape and out.dtype == np.uint8
+    assert mx <= 1 and frac < 2e-3, (mx, frac)
+    same_obj = filters.apply_filter("bilateral", img, img, sc, ss)   # aliased joint: one staged window
+    assert np.array_equal(same_obj, out)
+
+
+def test_bf_golden_gray_and_small(G):
+    g = G["bf_gray_in"]
+    out = filters.apply_filter("bilateral", g, g.copy(), 20, 22)     # takes the single-channel kernel
+    mx, frac = lsb_stats(out, G["bf_gray_c20_s22"])
+    assert mx <= 1 and frac < 2e-3, (mx, frac)
+    assert np.array_equal(out[:, :, 0], out[:, :, 1]) and np.array_equal(out[:, :, 0], out[:, :, 2])
+    s = G["bf_stress_in"]                                            # 20x24 image, radius 33
+    mx, frac = lsb_stats(filters.apply_filter("bilateral", s, s.copy(), 20, 22), G["bf_stress_c20_s22"])
+    assert mx <= 1 and frac < 5e-3, (mx, frac)
+
+
+@pytest.mark.parametrize("h,w", [(96, 80), (33, 131), (8, 300), (1, 1), (2, 5)])
+def test_bf_joint_differs_from_src(h, w):
+    joint = synth.natural(h, w, 10)
+    src = synth.stress(h, w, 11)
+    out = filters.apply_filter("bilateral", src, joint, 20, 22)
+    mx, frac = lsb_stats(out, oracle.joint_bilateral(joint, src, -1, 20, 22))
+    assert mx <= 1 and frac < 2e-3, (mx, frac)
+
+
+def test_bf_channel_combinations():
+    joint = synth.natural(40, 56, 20)
+    src = synth.natural(40, 56, 21)
+    dj, ds = dev_u8(joint[None]), dev_u8(src[None])
+    for jt, st, oj, os_ in [(dj[..., :1].contiguous(), ds, joint[:, :, :1], src),
+                            (dj, ds[..., 0].contiguous(), joint, src[:, :, 0]),
+                            (dj[..., 0].contiguous(), ds[..., 0].contiguous(), joint[:, :, 0], src[:, :, 0])]:
+        out = filters.joint_bilateral_device(jt, st, 20, 22).cpu().numpy()[0]
+        ref = oracle.joint_bilateral(oj, os_, -1, 20, 22)
+        mx, frac = lsb_stats(out.reshape(ref.shape), ref)
+        assert mx <= 1 and frac < 2e-3, (mx, frac)
+    # explicit d overrides the radius
+    out = filters.joint_bilateral_device(dj, ds, 20, 22, d=9).cpu().numpy()[0]
+    mx, frac = lsb_stats(out, oracle.joint_bilateral(joint, src, 9, 20, 22))
+    assert mx <= 1 and frac < 2e-3
+
+
+def test_bf_full_size_config1_properties_and_oracle():
+    # BASELINE config 1: 512x384, c20 s22, a copy of itself as joint
+    img = synth.natural(384, 512, 1000)
+    out = filters.apply_filter("bilateral", img, img.copy(), 20, 22)
+    ref = oracle.joint_bilateral(img.copy(), img, -1, 20, 22)
+    mx, frac = lsb_stats(out, ref)
+    assert mx <= 1 and frac < 1e-3, (mx, frac)
+    const = np.full((384, 512, 3), 200, np.uint8)                    # constants are fixed points
+    assert np.array_equal(filters.apply_filter("bilateral", const, img, 20, 22), const)
+    gsrc = np.repeat(img[:, :, :1], 3, axis=2)                       # equal src channels stay equal
+    o = filters.apply_filter("bilateral", gsrc, img, 20, 22)
+    assert np.array_equal(o[:, :, 0], o[:, :, 1]) and np.array_equal(o[:, :, 0], o[:, :, 2])
+
+
+def test_bf_batch_equals_per_image_and_radius_limit():
+    imgs = synth.batch("natural", 3, 64, 72, 6)
+    d = dev_u8(imgs)
+    batch = filters.joint_bilateral_device(d, d, 15, 28).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(batch[i], filters.apply_filter("bilateral", imgs[i], imgs[i], 15, 28))
+    from reflectance_filtering_b200 import _native
+    with pytest.raises(_native.NativeError, match="radius"):
+        filters.joint_bilateral_device(d, d, 20, 200.0)
+
+
+# ---- guided filter -----------------------------------------------------------------------------
+@pytest.mark.parametrize("h,w,r,eps,sc", [(96, 120, 45, 3.0, 3), (72, 60, 7, 3.0, 3), (64, 64, 52, 7.0, 1),
+                                          (30, 700, 45, 3.0, 1), (5, 3, 2, 0.5, 3), (1, 1, 1, 1.0, 3)])
+def test_gf_matches_oracle(h, w, r, eps, sc):
+    gd = synth.flat(h, w, 51)
+    src = synth.natural(h, w, 52)
+    if sc == 1:
+        src = src[:, :, 0]
+    out = filters.apply_filter("guided", src, gd, eps, float(r) + 0.7)   # radius = int(sigma_spatial)
+    ref = oracle.guided(gd, src, r, eps)
+    mx, frac = lsb_stats(out, ref)
+    assert out.shape == ref.shape and mx <= 1 and frac < 2e-3, (mx, frac)
+
+
+def test_gf_full_size_three_iterations_and_properties(net):
+    # BASELINE config 3 on one image: CNN reflectance, 'flat' guide, c3 s45, 3 iterations with uint8
+    # re-quantisation between them
+    img = synth.natural(384, 512, 3000)
+    gd = synth.flat(384, 512, 3500)
+    pipe = pipeline.Pipeline(net)
+    out = pipe.cnn_gf(dev_u8(img[None]), dev_u8(gd[None]), 3.0, 45.0, iterations=3).cpu().numpy()[0]
+    cur = (cnn.get_reflectance_caffe(net, img) * 255).astype(np.uint8)
+    for _ in range(3):
+        cur = oracle.guided(gd, cur, 45, 3.0)
+    mx, frac = lsb_stats(out, cur)
+    assert mx <= 1 and frac < 5e-3, (mx, frac)
+    const = np.full((384, 512, 3), 131, np.uint8)
+    assert np.array_equal(filters.apply_filter("guided", const, gd, 3.0, 45.0), const)
+    g3 = np.repeat(cur[:, :, None], 3, axis=2)                      # replicated src == 1-channel path
+    o3 = filters.apply_filter("guided", g3, gd, 3.0, 45.0)
+    o1 = filters.apply_filter("guided", cur, gd, 3.0, 45.0)
+    assert all(np.array_equal(o3[:, :, c], o1) for c in range(3))
+
+
+# ---- pipeline, CLI, sharding ---------------------------------------------------------------------
+def test_pipeline_cnn_bf_config2(net, mlp):
+    img = synth.natural(384, 512, 2000)
+    pipe = pipeline.Pipeline(net)
+    out = pipe.cnn_bf(dev_u8(img[None]), 20.0, 22.0).cpu().numpy()[0]
+    r8 = oracle.quantize_trunc(oracle.mlp_forward(mlp, img))
+    r8_gpu = pipe.reflectance_u8(dev_u8(img[None])).cpu().numpy()[0]
+    mx, frac = lsb_stats(r8_gpu, r8)
+    assert mx <= 1 and frac < 1e-3
+    g3 = np.repeat(r8_gpu[:, :, None], 3, axis=2)                   # what cv2.imread makes of <base>-r.png
+    ref = oracle.joint_bilateral(g3.copy(), g3, -1, 20, 22)[:, :, 0]
+    mx, frac = lsb_stats(out, ref)
+    assert mx <= 1 and frac < 1e-3, (mx, frac)
+
+
+def test_run_host_equals_device_path(net):
+    imgs = synth.batch("natural", 5, 48, 64, 8)
+    pipe = pipeline.Pipeline(net)
+    want = pipe.cnn_bf(dev_u8(imgs), 20.0, 22.0).cpu().numpy()
+    pin_in = torch.from_numpy(imgs).pin_memory()
+    pin_out = torch.empty((5, 48, 64), dtype=torch.uint8).pin_memory()
+    pipe.run_host("cnn_bf", pin_in, pin_out, chunk=2, n_streams=2, sigma_color=20.0, sigma_spatial=22.0)
+    assert np.array_equal(pin_out.numpy(), want)
+    # sharded == unsharded, independent of shard order
+    parts = {}
+    for rank in (1, 0):
+        lo, hi = pipeline.shard_range(5, rank, 2)
+        parts[rank] = pipe.cnn_bf(dev_u8(imgs[lo:hi]), 20.0, 22.0).cpu().numpy()
+    assert np.array_equal(np.concatenate([parts[0], parts[1]]), want)
+    st = pipeline.aggregate_stats(dev_u8(imgs[..., 0]), dev_u8(want))
+    assert st[0] == want.size and st[1] == float(want.astype(np.float64).sum())
+    assert st[3] == float(np.abs(want.astype(np.int64) - imgs[..., 0].astype(np.int64)).sum())
+
+
+def test_cli_end_to_end(tmp_path, net, mlp):
+    import cv2
+    img = synth.natural(60, 84, 9)
+    fin = str(tmp_path / "photo.png")
+    cv2.imwrite(fin, img)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    subprocess.run([sys.executable, os.path.join(ROOT, "decompose_with_trained_CNN.py"), "--filename_in", fin,
+                    "--path_out", str(tmp_path)], check=True, env=env, timeout=600)
+    for suffix in ("-r.png", "-r_colorized.png", "-s_colorized.png"):
+        assert os.path.exists(str(tmp_path / ("photo" + suffix)))
+    r_png = cv2.imread(str(tmp_path / "photo-r.png"), cv2.IMREAD_UNCHANGED)
+    assert r_png.ndim == 2
+    mx, frac = lsb_stats(r_png, oracle.quantize_trunc(oracle.mlp_forward(mlp, img)))
+    assert mx <= 1 and frac < 2e-3
+    # colorized outputs follow the reference conventions applied to our reflectance
+    gray = cnn.get_reflectance_caffe(net, img)
+    refl, shad = iu.colorize(gray, img)
+    assert np.array_equal(cv2.imread(str(tmp_path / "photo-r_colorized.png"), cv2.IMREAD_UNCHANGED),
+                          iu.quantize(refl, sRGB=True))
+    subprocess.run([sys.executable, os.path.join(ROOT, "filter_reflectance.py"), "--filter_type=bilateral",
+                    "--sigma_color=20", "--sigma_spatial=22", "--filename_in", str(tmp_path / "photo-r.png"),
+                    "--guidance_in", str(tmp_path / "photo-r.png"), "--path_out", str(tmp_path)],
+                   check=True, env=env, timeout=600)
+    fout = str(tmp_path / "photo-r_bilateral_c20.0s22.0.png")
+    assert os.path.exists(fout)
+    got = cv2.imread(fout)
+    g3 = cv2.imread(str(tmp_path / "photo-r.png"))
+    mx, frac = lsb_stats(got, oracle.joint_bilateral(g3.copy(), g3, -1, 20, 22))
+    assert mx <= 1 and frac < 2e-3
+    subprocess.run([sys.executable, os.path.join(ROOT, "filter_reflectance.py"), "--filter_type=guided",
+                    "--sigma_color=3", "--sigma_spatial=45", "--filename_in", str(tmp_path / "photo-r.png"),
+                    "--guidance_in", fin, "--path_out", str(tmp_path)], check=True, env=env, timeout=600)
+    got = cv2.imread(str(tmp_path / "photo-r_guided_c3.0s45.0.png"))
+    mx, frac = lsb_stats(got, oracle.guided(img, g3, 45, 3.0))
+    assert mx <= 1 and frac < 2e-3
+
+
+def test_native_library_is_the_one_loaded():
+    from reflectance_filtering_b200 import _native
+    before = _native.launch_count()
+    img = synth.natural(16, 16, 1)
+    filters.apply_filter("bilateral", img, img, 20, 22)
+    assert _native.launch_count() > before
+    maps = open("/proc/self/maps").read()
+    assert "librf_b200.so" in maps
