@@ -267,6 +267,35 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     cnn_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bf_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
 
+    # ---- configs[2]: CNN -> GF(CNN, flat) c3 s45 x3, batch of 64 (secondary line, same JSON) ----------
+    gf = None
+    if not args.no_gf:
+        GB = args.gf_batch
+        flat = np.stack([synth.flat(H, W, 1000 * 3 + 500 + rank * GB + i) for i in range(min(GB, 16))])
+        d_flat = torch.from_numpy(np.stack([flat[i % len(flat)] for i in range(GB)])).to(device)
+        d_imgs = dev_pool[0][:GB] if GB <= B else dev_pool.reshape(-1, H, W, 3)[:GB]
+        for _ in range(2):
+            pipe.cnn_gf(d_imgs, d_flat, 3.0, 45.0, iterations=3)
+        g_steps = max(3, args.steps // 4)
+        barrier()
+        e0.record()
+        for _ in range(g_steps):
+            pipe.cnn_gf(d_imgs, d_flat, 3.0, 45.0, iterations=3)
+        e1.record()
+        barrier()
+        gf_ms = max_over_ranks(e0.elapsed_time(e1)) / g_steps
+        r8 = pipe.reflectance_u8(d_imgs)
+        gev = [torch.cuda.Event(enable_timing=True) for _ in range(g_steps + 1)]
+        tmp = None
+        barrier()
+        gev[0].record()
+        for i in range(g_steps):
+            tmp = filters.guided_device(d_flat, r8, 45, 3.0, out=tmp)
+            gev[i + 1].record()
+        barrier()
+        gf_iter_ms = float(np.mean([gev[i].elapsed_time(gev[i + 1]) for i in range(g_steps)]))
+        gf = {"ms_per_step": gf_ms, "gf_iteration_ms": gf_iter_ms, "batch": GB, "steps": g_steps}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -325,6 +354,20 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         "roofline_cnn": cnn_roof,
         "cpu_baseline": cpu,
     }
+    if gf is not None:
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        gpx = gf["batch"] * H * W
+        # algorithmic bytes per pixel per iteration, 1-channel src: pass A reads 3 (guide)
+        # + 1 (src) and writes 16 (a0,a1,a2,b); pass B reads 16 + 3 (guide) and writes 1  => 40 B/px
+        bpp = 40.0
+        ach = gpx * bpp / (gf["gf_iteration_ms"] * 1e-3) / 1e9
+        line["config3_cnn_gf_x3"] = {
+            "workload": "configs[2]: %d x 512x384, CNN -> GF(CNN, flat guide) c3.0 s45.0 (r=45), 3 iterations, "
+                        "uint8 re-quantisation between iterations" % gf["batch"],
+            "value": world * gpx / (gf["ms_per_step"] * 1e-3) / 1e6, "unit": "MP/s", "ms_per_step": gf["ms_per_step"],
+            "roofline": {"kernel": "gf_pass_a<1> + gf_pass_b<1> (one iteration)", "bound": "hbm", "achieved": ach,
+                         "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "bytes_per_pixel": bpp,
+                         "launch_ms": gf["gf_iteration_ms"], "traffic": None, "peak_source": peak_src}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -340,6 +383,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=16, help="images per H2D/compute/D2H chunk in the e2e path")
     ap.add_argument("--cpu-images", type=int, default=6, help="sample size of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gf", action="store_true", help="skip the secondary configs[2] (CNN->GF x3) measurement")
+    ap.add_argument("--gf-batch", type=int, default=64)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

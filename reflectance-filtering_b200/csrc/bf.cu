@@ -350,13 +350,20 @@ static size_t smem_bytes(int wy, const Geometry &g, bool sep)
 template <typename K>
 static int launch(K kernel, int wy, const Args &a, size_t smem, cudaStream_t st, const char *name)
 {
-    // opt in to large dynamic shared memory once per (instantiation, device)
-    static bool configured[64] = {};
+    // opt in to large dynamic shared memory once per (kernel instantiation, device); K is the same
+    // function-pointer type for every instantiation, so the record is keyed by the pointer value
+    static std::mutex mu;
+    static std::vector<std::pair<const void *, int>> configured;
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured[dev & 63] = true;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        bool done = false;
+        for (const auto &c : configured) done |= (c.first == (const void *)kernel && c.second == dev);
+        if (!done) {
+            RF_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            configured.emplace_back((const void *)kernel, dev);
+        }
     }
     dim3 grid((a.w + TW - 1) / TW, (a.h + ROWS_PER_WARP * wy - 1) / (ROWS_PER_WARP * wy), a.n);
     kernel<<<grid, 32 * wy, smem, st>>>(a);
