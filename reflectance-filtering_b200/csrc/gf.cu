@@ -18,6 +18,7 @@
 // hop) followed by P[x+r] - P[x-r-1].  All elementwise FP32 math uses the non-contracting
 // __fmul_rn/__fadd_rn forms so pass A reproduces the oracle's separate multiply/add bit for bit.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -311,6 +312,14 @@ static int run(Args a, cudaStream_t st)
 }  // namespace gf
 }  // namespace rf
 
+namespace rf {
+namespace gf2 {  // gf2.cu: strip kernels for radius <= 64
+bool supported(int r);
+int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, float *ab, int n, int h, int w, int r,
+        double eps, cudaStream_t st);
+}  // namespace gf2
+}  // namespace rf
+
 using namespace rf;
 
 extern "C" int rf_guided_max_radius(void) { return gf::MAX_RADIUS; }
@@ -325,6 +334,18 @@ extern "C" size_t rf_guided_workspace_bytes(int sc, int n, int h, int w, int rad
     const size_t cap = (size_t)8 << 30;
     if (want > cap) want = (cap / per > 0 ? cap / per : 1) * per;
     return want;
+}
+
+// RF_GF_GENERIC=1 in the environment forces the generic (any radius, FP64 box mean) kernels: used by the
+// tests to cross-check the two implementations against each other.
+static int flags_generic_path()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RF_GF_GENERIC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
 }
 
 extern "C" int rf_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst, int n, int h,
@@ -346,9 +367,17 @@ extern "C" int rf_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, in
     int chunk = (int)(ws_bytes / per < (size_t)n ? ws_bytes / per : (size_t)n);
     if (chunk > 65535) chunk = 65535;
     const size_t img_px = (size_t)h * w;
+    const bool generic = !gf2::supported(radius) || (flags_generic_path() != 0);
     for (int i0 = 0; i0 < n; i0 += chunk) {
+        const int nn = n - i0 < chunk ? n - i0 : chunk;
+        if (!generic) {
+            int rc = gf2::run(guide + i0 * img_px * 3, src + i0 * img_px * sc, sc, dst + i0 * img_px * sc, (float *)ws,
+                              nn, h, w, radius, eps, (cudaStream_t)stream);
+            if (rc != RF_OK) return rc;
+            continue;
+        }
         gf::Args a;
-        a.n = n - i0 < chunk ? n - i0 : chunk;
+        a.n = nn;
         a.guide = guide + i0 * img_px * 3;
         a.src = src + i0 * img_px * sc;
         a.dst = dst + i0 * img_px * sc;

@@ -1,0 +1,463 @@
+// Guided filter, fast path for radius <= 64: strip kernels with per-lane column chunks.
+//
+// Same semantics as gf.cu (ximgproc guidedFilter; call site
+// /root/reference/filter_reflectance.py:67-70).  What changes is the work decomposition, chosen from
+// the measured pipe rates on B200 (profiles/r01_microbench_pipes.txt): SHFL, I2F and anything FP64 issue
+// at 1/4 to 1/8 of the FP32 rate, so
+//   * every lane owns C consecutive columns of a 32*C wide strip and keeps the vertical window sums of
+//     its quantities in FP32 registers -- they are integers below 2^23 ((2r+1)*255^2 for r <= 64), so
+//     the FFMA updates (add the entering row, subtract the leaving one) are exact;
+//   * the horizontal direction is a per-lane serial prefix over its C columns plus ONE 5-step warp
+//     scan of the lane totals per quantity (uint32, wrap-around safe): 5/C shuffles per column;
+//   * the quantities are split over the warps of the CTA (each warp scans the whole strip width for
+//     its 3-4 quantities); prefixes go to a double-buffered shared-memory row, and after ONE
+//     __syncthreads per row all threads turn P[x+r] - P[x-r-1] into means, solve the 3x3 system with
+//     the oracle's non-contracted multiply/add order and store the coefficient planes;
+//   * no FP64: the box mean is float(S) * float(1/k^2) (<= 1 ulp from OpenCV's float(double(S)/k^2);
+//     measured effect ~2.5e-5 of the output bytes move by 1 LSB); pass B accumulates the
+//     coefficient planes in FP32 the same way.
+// Coefficient planes are planar: ab[n][SC][4][h][w] = (a0, a1, a2, b).
+#include "common.cuh"
+
+namespace rf {
+namespace gf2 {
+
+constexpr int MAX_RADIUS = 64;  // (2r+1) * 65025 < 2^23
+constexpr int QMAX = 21;
+
+struct Args {
+    const uint8_t *guide;  // [n][h][w][3]
+    const uint8_t *src;    // [n][h][w][SC]
+    float *ab;             // [n][SC][4][h][w]
+    uint8_t *dst;          // [n][h][w][SC]
+    int n, h, w, r;
+    int rh;          // halo columns on each side of a strip: round_up(r + 1, 4)
+    int twe;         // output columns per strip (multiple of 4)
+    int seg_rows;    // output rows per CTA
+    float eps;
+    float inv_area;  // 1 / (2r+1)^2
+    int fast_loads;  // w % 4 == 0 and 16-byte aligned base pointers: 32-bit loads of pixel chunks
+};
+
+__device__ __forceinline__ float b2f(uint32_t word, int byte)
+{
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u | (uint32_t)byte)) - 8388608.0f;
+}
+
+// C pixels [gx0, gx0 + C) of one image row as floats ch[c][k], k < CN
+template <int C, int CN>
+__device__ __forceinline__ void load_chunk(const uint8_t *row, int gx0, int w, bool fast, float (&ch)[C][CN])
+{
+    if (fast && gx0 >= 0 && gx0 + C <= w) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)gx0 * CN);
+        uint32_t wd[C * CN / 4];
+#pragma unroll
+        for (int i = 0; i < C * CN / 4; ++i) wd[i] = __ldg(p + i);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int k = 0; k < CN; ++k) {
+                const int byte = c * CN + k;
+                ch[c][k] = b2f(wd[byte >> 2], byte & 3);
+            }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const uint8_t *px = row + (size_t)reflect(gx0 + c, w) * CN;
+#pragma unroll
+            for (int k = 0; k < CN; ++k) ch[c][k] = (float)px[k];
+        }
+    }
+}
+
+// channel ids: 0..2 guide, 3..5 source, 6 = the constant 1.  Quantity q is ch[qa(q)] * ch[qb(q)].
+// Order = the m[] layout of the solve: I (3), I*I' (6), then per source channel p, p*I0, p*I1, p*I2.
+__host__ __device__ constexpr int qa(int q)
+{
+    constexpr int t[QMAX] = {0, 1, 2, 0, 0, 0, 1, 1, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5};
+    return t[q];
+}
+__host__ __device__ constexpr int qb(int q)
+{
+    constexpr int t[QMAX] = {6, 6, 6, 0, 1, 2, 1, 2, 2, 6, 0, 1, 2, 6, 0, 1, 2, 6, 0, 1, 2};
+    return t[q];
+}
+__host__ __device__ constexpr bool q_is_linear(int q) { return qb(q) == 6; }
+
+constexpr int NQG = 4;  // most quantities any warp owns
+
+template <int SC, int C, int Q0, int NQ>
+__device__ __forceinline__ void accumulate(float (&V)[NQG][C], const Args &g, const uint8_t *G, const uint8_t *S,
+                                           int yy, int gx0, bool fast, float sign)
+{
+    float gch[C][3], sch[C][SC];
+    load_chunk<C, 3>(G + (size_t)yy * g.w * 3, gx0, g.w, fast, gch);
+    load_chunk<C, SC>(S + (size_t)yy * g.w * SC, gx0, g.w, fast, sch);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float ch[7];
+        ch[0] = gch[c][0];
+        ch[1] = gch[c][1];
+        ch[2] = gch[c][2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ch[3 + k] = k < SC ? sch[c][k] : 0.0f;
+        ch[6] = 1.0f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) V[q][c] = fmaf(sign * ch[qa(Q0 + q)], ch[qb(Q0 + q)], V[q][c]);
+    }
+}
+
+// per-lane serial prefix + warp scan of the lane totals; inclusive strip-wide prefixes to shared memory
+template <int C, int Q0, int NQ>
+__device__ __forceinline__ void scan_store(const float (&V)[NQG][C], uint32_t *P, int nx, int lane)
+{
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        uint32_t pre[C];
+        uint32_t run = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            run += __float_as_uint(V[q][c] + 8388608.0f);  // integer value + 0x4B000000 per element
+            pre[c] = run;
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t excl = incl - run;
+        uint32_t *dst = P + (Q0 + q) * nx + lane * C;
+#pragma unroll
+        for (int c = 0; c < C; c += 4)
+            *reinterpret_cast<uint4 *>(dst + c) =
+                make_uint4(pre[c] + excl, pre[c + 1] + excl, pre[c + 2] + excl, pre[c + 3] + excl);
+    }
+}
+
+// warp-uniform dispatch of the per-group templates
+#define RF_GF2_GROUPS_1(FN, ...)                          \
+    switch (group) {                                      \
+        case 0: FN<SC, C, 0, 3>(__VA_ARGS__); break;      \
+        case 1: FN<SC, C, 3, 3>(__VA_ARGS__); break;      \
+        case 2: FN<SC, C, 6, 3>(__VA_ARGS__); break;      \
+        default: FN<SC, C, 9, 4>(__VA_ARGS__); break;     \
+    }
+#define RF_GF2_GROUPS_3(FN, ...)                          \
+    switch (group) {                                      \
+        case 0: FN<SC, C, 0, 3>(__VA_ARGS__); break;      \
+        case 1: FN<SC, C, 3, 3>(__VA_ARGS__); break;      \
+        case 2: FN<SC, C, 6, 3>(__VA_ARGS__); break;      \
+        case 3: FN<SC, C, 9, 4>(__VA_ARGS__); break;      \
+        case 4: FN<SC, C, 13, 4>(__VA_ARGS__); break;     \
+        default: FN<SC, C, 17, 4>(__VA_ARGS__); break;    \
+    }
+
+template <int SC, int C, int Q0, int NQ>
+__device__ __forceinline__ void scan_store_sc(const float (&V)[NQG][C], uint32_t *P, int nx, int lane)
+{
+    scan_store<C, Q0, NQ>(V, P, nx, lane);
+}
+
+template <int SC>
+__host__ __device__ constexpr int n_groups() { return SC == 1 ? 4 : 6; }
+
+// ---- pass A ---------------------------------------------------------------------------------------
+template <int SC, int C>
+__global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args g)
+{
+    constexpr int Q = 9 + 4 * SC, NX = 32 * C, NT = 32 * n_groups<SC>();
+    extern __shared__ __align__(16) uint32_t pbuf[];  // [2][Q][NX]
+    const int tid = threadIdx.x, lane = tid & 31, group = tid >> 5;
+    const int img = blockIdx.z;
+    const int sx0 = blockIdx.x * g.twe;
+    const int y0 = blockIdx.y * g.seg_rows;
+    const int y1 = min(g.h, y0 + g.seg_rows);
+    const int gx0 = sx0 - g.rh + lane * C;
+    const bool fast = g.fast_loads != 0;
+    const size_t img_px = (size_t)g.h * g.w;
+    const uint8_t *G = g.guide + img * img_px * 3;
+    const uint8_t *S = g.src + img * img_px * SC;
+    const int r = g.r;
+    const int n_out = min(g.twe, g.w - sx0);
+    const uint32_t bias = (uint32_t)(2 * r + 1) * 0x4B000000u;  // what the biased elements add to a window
+
+    float V[NQG][C];
+#pragma unroll
+    for (int q = 0; q < NQG; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) V[q][c] = 0.0f;
+
+    for (int dy = -r; dy < r; ++dy) {
+        const int yy = reflect(y0 + dy, g.h);
+        if (SC == 1) { RF_GF2_GROUPS_1(accumulate, V, g, G, S, yy, gx0, fast, 1.0f) }
+        else { RF_GF2_GROUPS_3(accumulate, V, g, G, S, yy, gx0, fast, 1.0f) }
+    }
+    for (int y = y0; y < y1; ++y) {
+        {
+            const int yy = reflect(y + r, g.h);
+            if (SC == 1) { RF_GF2_GROUPS_1(accumulate, V, g, G, S, yy, gx0, fast, 1.0f) }
+            else { RF_GF2_GROUPS_3(accumulate, V, g, G, S, yy, gx0, fast, 1.0f) }
+        }
+        uint32_t *P = pbuf + ((y - y0) & 1) * (Q * NX);
+        if (SC == 1) { RF_GF2_GROUPS_1(scan_store_sc, V, P, NX, lane) }
+        else { RF_GF2_GROUPS_3(scan_store_sc, V, P, NX, lane) }
+        // One barrier per row: prefixes of row y are visible, and every thread has finished the math of
+        // row y-1 (so the buffer written two rows from now is free).
+        __syncthreads();
+
+        for (int idx = tid; idx < n_out; idx += NT) {
+            const int i = g.rh + idx;
+            float m[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const uint32_t s = P[q * NX + i + r] - P[q * NX + i - r - 1] - bias;
+                // sums of single channels stay below 2^23: exact integer->float on the FMA pipe
+                const float sf = q_is_linear(q) ? __uint_as_float(s | 0x4B000000u) - 8388608.0f : (float)s;
+                m[q] = __fmul_rn(sf, g.inv_area);
+            }
+            // cov(I) + eps*Id, symmetric storage 0:(0,0) 1:(0,1) 2:(0,2) 3:(1,1) 4:(1,2) 5:(2,2)
+            const float c00 = __fadd_rn(__fsub_rn(m[3], __fmul_rn(m[0], m[0])), g.eps);
+            const float c01 = __fsub_rn(m[4], __fmul_rn(m[0], m[1]));
+            const float c02 = __fsub_rn(m[5], __fmul_rn(m[0], m[2]));
+            const float c11 = __fadd_rn(__fsub_rn(m[6], __fmul_rn(m[1], m[1])), g.eps);
+            const float c12 = __fsub_rn(m[7], __fmul_rn(m[1], m[2]));
+            const float c22 = __fadd_rn(__fsub_rn(m[8], __fmul_rn(m[2], m[2])), g.eps);
+            const float f00 = __fsub_rn(__fmul_rn(c11, c22), __fmul_rn(c12, c12));
+            const float f01 = __fsub_rn(__fmul_rn(c12, c02), __fmul_rn(c01, c22));
+            const float f02 = __fsub_rn(__fmul_rn(c01, c12), __fmul_rn(c11, c02));
+            const float f11 = __fsub_rn(__fmul_rn(c22, c00), __fmul_rn(c02, c02));
+            const float f12 = __fsub_rn(__fmul_rn(c02, c01), __fmul_rn(c12, c00));
+            const float f22 = __fsub_rn(__fmul_rn(c00, c11), __fmul_rn(c01, c01));
+            float det = __fmul_rn(c00, f00);
+            det = __fadd_rn(det, __fmul_rn(c01, f01));
+            det = __fadd_rn(det, __fmul_rn(c02, f02));
+            if (g.eps < 1e-2f && fabsf(det) < 1e-6f) det = 1e-6f;
+            // one correctly rounded reciprocal instead of six divisions: each entry is within 1 ulp of cof/det
+            const float rdet = __frcp_rn(det);
+            const float i00 = __fmul_rn(f00, rdet), i01 = __fmul_rn(f01, rdet), i02 = __fmul_rn(f02, rdet);
+            const float i11 = __fmul_rn(f11, rdet), i12 = __fmul_rn(f12, rdet), i22 = __fmul_rn(f22, rdet);
+            const size_t opix = (size_t)y * g.w + sx0 + idx;
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                const float mp = m[9 + 4 * c];
+                const float k0 = __fsub_rn(m[10 + 4 * c], __fmul_rn(mp, m[0]));
+                const float k1 = __fsub_rn(m[11 + 4 * c], __fmul_rn(mp, m[1]));
+                const float k2 = __fsub_rn(m[12 + 4 * c], __fmul_rn(mp, m[2]));
+                float a0 = __fmul_rn(i00, k0);
+                a0 = __fadd_rn(a0, __fmul_rn(i01, k1));
+                a0 = __fadd_rn(a0, __fmul_rn(i02, k2));
+                float a1 = __fmul_rn(i01, k0);
+                a1 = __fadd_rn(a1, __fmul_rn(i11, k1));
+                a1 = __fadd_rn(a1, __fmul_rn(i12, k2));
+                float a2 = __fmul_rn(i02, k0);
+                a2 = __fadd_rn(a2, __fmul_rn(i12, k1));
+                a2 = __fadd_rn(a2, __fmul_rn(i22, k2));
+                float b = __fsub_rn(mp, __fmul_rn(a0, m[0]));
+                b = __fsub_rn(b, __fmul_rn(a1, m[1]));
+                b = __fsub_rn(b, __fmul_rn(a2, m[2]));
+                float *o = g.ab + ((size_t)(img * SC + c) * 4) * img_px + opix;
+                o[0] = a0;
+                o[img_px] = a1;
+                o[2 * img_px] = a2;
+                o[3 * img_px] = b;
+            }
+        }
+        {
+            const int yy = reflect(y - r, g.h);
+            if (SC == 1) { RF_GF2_GROUPS_1(accumulate, V, g, G, S, yy, gx0, fast, -1.0f) }
+            else { RF_GF2_GROUPS_3(accumulate, V, g, G, S, yy, gx0, fast, -1.0f) }
+        }
+    }
+}
+
+// ---- pass B ---------------------------------------------------------------------------------------
+// one warp per coefficient plane (4 * SC warps); FP32 vertical sliding sums and FP32 prefixes
+template <int C>
+__device__ __forceinline__ void load_plane_chunk(const float *row, int gx0, int w, bool fast, float (&v)[C])
+{
+    if (fast && gx0 >= 0 && gx0 + C <= w) {
+#pragma unroll
+        for (int c = 0; c < C; c += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(row + gx0 + c));
+            v[c] = t.x;
+            v[c + 1] = t.y;
+            v[c + 2] = t.z;
+            v[c + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = row[reflect(gx0 + c, w)];
+    }
+}
+
+template <int SC, int C>
+__global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
+{
+    constexpr int Q = 4 * SC, NX = 32 * C, NT = 32 * Q;
+    extern __shared__ __align__(16) float fbuf[];  // [2][Q][NX]
+    const int tid = threadIdx.x, lane = tid & 31, plane = tid >> 5;
+    const int img = blockIdx.z;
+    const int sx0 = blockIdx.x * g.twe;
+    const int y0 = blockIdx.y * g.seg_rows;
+    const int y1 = min(g.h, y0 + g.seg_rows);
+    const int gx0 = sx0 - g.rh + lane * C;
+    const bool fast = g.fast_loads != 0;
+    const size_t img_px = (size_t)g.h * g.w;
+    const float *A = g.ab + ((size_t)img * Q + plane) * img_px;
+    const int r = g.r;
+    const int n_out = min(g.twe, g.w - sx0);
+
+    float V[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) V[c] = 0.0f;
+    auto add_row = [&](int yy, float sign) {
+        float v[C];
+        load_plane_chunk<C>(A + (size_t)yy * g.w, gx0, g.w, fast, v);
+#pragma unroll
+        for (int c = 0; c < C; ++c) V[c] = fmaf(sign, v[c], V[c]);
+    };
+    for (int dy = -r; dy < r; ++dy) add_row(reflect(y0 + dy, g.h), 1.0f);
+    for (int y = y0; y < y1; ++y) {
+        add_row(reflect(y + r, g.h), 1.0f);
+        float *P = fbuf + ((y - y0) & 1) * (Q * NX);
+        {
+            float pre[C];
+            float run = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                run += V[c];
+                pre[c] = run;
+            }
+            float incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const float excl = incl - run;
+            float *dst = P + plane * NX + lane * C;
+#pragma unroll
+            for (int c = 0; c < C; c += 4)
+                *reinterpret_cast<float4 *>(dst + c) =
+                    make_float4(pre[c] + excl, pre[c + 1] + excl, pre[c + 2] + excl, pre[c + 3] + excl);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n_out; idx += NT) {
+            const int i = g.rh + idx;
+            const size_t opix = (size_t)y * g.w + sx0 + idx;
+            const uint8_t *gp = g.guide + (img * img_px + opix) * 3;
+            const float i0 = gp[0], i1 = gp[1], i2 = gp[2];
+            uint8_t *o = g.dst + (img * img_px + opix) * SC;
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                float m[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float *Pq = P + (4 * c + k) * NX;
+                    m[k] = __fmul_rn(Pq[i + r] - Pq[i - r - 1], g.inv_area);
+                }
+                float v = m[3];
+                v = __fadd_rn(v, __fmul_rn(m[0], i0));
+                v = __fadd_rn(v, __fmul_rn(m[1], i1));
+                v = __fadd_rn(v, __fmul_rn(m[2], i2));
+                o[c] = sat_u8(v);
+            }
+        }
+        add_row(reflect(y - r, g.h), -1.0f);
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------
+struct Plan {
+    int C, strips, twe, rh, segs, seg_rows;
+};
+
+static Plan make_plan(int n, int h, int w, int r, int sms, int warps_per_cta)
+{
+    Plan best{};
+    long best_cost = -1;
+    const int rh = (r + 1 + 3) & ~3;
+    for (int C : {8, 12, 16}) {
+        const int tw = 32 * C - 2 * rh;
+        if (tw < 32) continue;
+        const int strips = (w + tw - 1) / tw;
+        int twe = ((w + strips - 1) / strips + 3) & ~3;
+        if (twe > tw) twe = tw & ~3;
+        const long cost = (long)strips * 32 * C;  // columns touched per image row
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = Plan{C, strips, twe, rh, 1, h};
+        }
+    }
+    // split rows when the grid cannot fill the SMs; every segment pays 2r rows of warm-up
+    const long ctas = (long)best.strips * n;
+    const long want = (long)sms * 16 / warps_per_cta;  // ~16 resident warps per SM
+    if (ctas < want) {
+        int segs = (int)((want + ctas - 1) / ctas);
+        const int max_segs = h / (4 * r + 2) > 1 ? h / (4 * r + 2) : 1;  // keep warm-up below ~50 %
+        if (segs > max_segs) segs = max_segs;
+        best.segs = segs;
+        best.seg_rows = (h + segs - 1) / segs;
+    }
+    return best;
+}
+
+template <int SC, int C>
+static int launch(Args a, const Plan &p, cudaStream_t st)
+{
+    constexpr int QA_ = 9 + 4 * SC, QB_ = 4 * SC, NX = 32 * C;
+    const size_t smem_a = (size_t)2 * QA_ * NX * sizeof(uint32_t);
+    const size_t smem_b = (size_t)2 * QB_ * NX * sizeof(float);
+    static bool configured[64] = {};
+    int dev = 0;
+    RF_CUDA_TRY(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RF_CUDA_TRY(cudaFuncSetAttribute(pass_b_kernel<SC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured[dev & 63] = true;
+    }
+    dim3 grid(p.strips, (a.h + p.seg_rows - 1) / p.seg_rows, a.n);
+    pass_a_kernel<SC, C><<<grid, 32 * n_groups<SC>(), smem_a, st>>>(a);
+    RF_LAUNCH_CHECK("gf2::pass_a_kernel");
+    pass_b_kernel<SC, C><<<grid, 32 * 4 * SC, smem_b, st>>>(a);
+    RF_LAUNCH_CHECK("gf2::pass_b_kernel");
+    return RF_OK;
+}
+
+bool supported(int r) { return r >= 1 && r <= MAX_RADIUS; }
+
+int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, float *ab, int n, int h, int w, int r,
+        double eps, cudaStream_t st)
+{
+    Args a;
+    a.guide = guide;
+    a.src = src;
+    a.ab = ab;
+    a.dst = dst;
+    a.n = n;
+    a.h = h;
+    a.w = w;
+    a.r = r;
+    a.eps = (float)eps;
+    const int k = 2 * r + 1;
+    a.inv_area = (float)(1.0 / ((double)k * k));
+    a.fast_loads = (w % 4 == 0) && ((uintptr_t)guide % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
+                   ((uintptr_t)ab % 16 == 0);
+    const Plan p = make_plan(n, h, w, r, sm_count(), sc == 1 ? 4 : 6);
+    a.rh = p.rh;
+    a.twe = p.twe;
+    a.seg_rows = p.seg_rows;
+#define RF_GF2_LAUNCH(SC_)                                       \
+    switch (p.C) {                                               \
+        case 8: return launch<SC_, 8>(a, p, st);                 \
+        case 12: return launch<SC_, 12>(a, p, st);               \
+        default: return launch<SC_, 16>(a, p, st);               \
+    }
+    if (sc == 1) { RF_GF2_LAUNCH(1) }
+    RF_GF2_LAUNCH(3)
+#undef RF_GF2_LAUNCH
+}
+
+}  // namespace gf2
+}  // namespace rf

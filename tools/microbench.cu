@@ -38,6 +38,13 @@ __global__ void probe(uint32_t *out, uint32_t seed, float fs)
             if (KIND == 7) a[i] = (a[i] + seed) ^ 0x5bd1e995u;                                 // IADD3+LOP3
             if (KIND == 8) f[i] = sm[(__float_as_uint(f[i]) >> 3) & 1023] + c1;                 // LDS random + FADD
             if (KIND == 9) f[i] = f[i] + c1;                                                   // FADD
+            if (KIND == 11) { double dd = (double)f[i]; f[i] = __uint_as_float((uint32_t)__double2hiint(dd)) ; }   // F2F.F64.F32 (+MOV)
+            if (KIND == 12) { double dd = (double)a[i]; a[i] = (uint32_t)__double2hiint(dd) + (uint32_t)__double2loint(dd); } // I2F.F64.U32 (+IADD)
+            if (KIND == 13) { double dd = __hiloint2double(a[i], a[i] ^ seed); f[i] = (float)dd; a[i] += 1; }    // F2F.F32.F64
+            if (KIND == 14) { double dd = __hiloint2double(0x40000000 | (a[i] & 0xffff), a[i]); dd = dd * 1.0000001 + 0.5; a[i] = (uint32_t)__double2hiint(dd) ^ (uint32_t)__double2loint(dd); } // DFMA
+            if (KIND == 15) { float t; asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(t) : "r"(a[i])); a[i] = __float_as_uint(t) >> 3; }  // I2FP.F32.U32 (+SHF)
+            if (KIND == 16) a[i] = __shfl_up_sync(0xffffffffu, a[i], 1) + 1;   // SHFL (+IADD)
+            if (KIND == 17) { sm[(threadIdx.x + it) & 1023] = f[i]; f[i] += c1; }    // STS.32 (+FADD)
             if (KIND == 10) { float4 v = *reinterpret_cast<float4 *>(&sm[((threadIdx.x * 4) + (it & 7) * 128) & 1020]); f[i] += v.x + v.w; } // LDS.128 + 2 FADD
         }
     }
@@ -94,5 +101,12 @@ int main()
     run<8>("LDS.32 random (+FADD,+2)", sms, 1);
     run<9>("FADD", sms, 1);
     run<10>("LDS.128 (+2 FADD)", sms, 1);
+    run<11>("F2F.F64.F32", sms, 1);
+    run<12>("I2F.F64.U32 (+IADD)", sms, 1);
+    run<13>("F2F.F32.F64 (+IADD)", sms, 1);
+    run<14>("DFMA (+LOP..)", sms, 1);
+    run<15>("I2FP.F32.U32 (+SHF)", sms, 1);
+    run<16>("SHFL.UP (+IADD)", sms, 1);
+    run<17>("STS.32 (+FADD)", sms, 1);
     return 0;
 }
