@@ -44,30 +44,43 @@ __device__ __forceinline__ float b2f(uint32_t word, int byte)
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u | (uint32_t)byte)) - 8388608.0f;
 }
 
-// C pixels [gx0, gx0 + C) of one image row as floats ch[c][k], k < CN
+// Raw bytes of the C pixels [gx0, gx0 + C) of one image row, packed into 32-bit words in memory order
+// (byte j of the chunk is byte j & 3 of word j >> 2).  Fast path: chunk inside the image and 4-byte
+// aligned -> plain 32-bit loads; border lanes assemble the same words from reflected byte loads.
 template <int C, int CN>
-__device__ __forceinline__ void load_chunk(const uint8_t *row, int gx0, int w, bool fast, float (&ch)[C][CN])
+struct RawChunk {
+    uint32_t w[C * CN / 4];
+};
+
+template <int C, int CN>
+__device__ __forceinline__ RawChunk<C, CN> load_raw(const uint8_t *row, int gx0, int w, bool fast)
 {
+    RawChunk<C, CN> r;
     if (fast && gx0 >= 0 && gx0 + C <= w) {
         const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)gx0 * CN);
-        uint32_t wd[C * CN / 4];
 #pragma unroll
-        for (int i = 0; i < C * CN / 4; ++i) wd[i] = __ldg(p + i);
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int k = 0; k < CN; ++k) {
-                const int byte = c * CN + k;
-                ch[c][k] = b2f(wd[byte >> 2], byte & 3);
-            }
+        for (int i = 0; i < C * CN / 4; ++i) r.w[i] = __ldg(p + i);
     } else {
+#pragma unroll
+        for (int i = 0; i < C * CN / 4; ++i) r.w[i] = 0u;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const uint8_t *px = row + (size_t)reflect(gx0 + c, w) * CN;
 #pragma unroll
-            for (int k = 0; k < CN; ++k) ch[c][k] = (float)px[k];
+            for (int k = 0; k < CN; ++k) {
+                const int byte = c * CN + k;
+                r.w[byte >> 2] |= (uint32_t)px[k] << (8 * (byte & 3));
+            }
         }
     }
+    return r;
+}
+
+template <int C, int CN>
+__device__ __forceinline__ float raw_channel(const RawChunk<C, CN> &r, int c, int k)
+{
+    const int byte = c * CN + k;
+    return b2f(r.w[byte >> 2], byte & 3);
 }
 
 // channel ids: 0..2 guide, 3..5 source, 6 = the constant 1.  Quantity q is ch[qa(q)] * ch[qb(q)].
@@ -86,21 +99,34 @@ __host__ __device__ constexpr bool q_is_linear(int q) { return qb(q) == 6; }
 
 constexpr int NQG = 4;  // most quantities any warp owns
 
-template <int SC, int C, int Q0, int NQ>
-__device__ __forceinline__ void accumulate(float (&V)[NQG][C], const Args &g, const uint8_t *G, const uint8_t *S,
-                                           int yy, int gx0, bool fast, float sign)
+// one image row's guide + source chunk of this lane, in flight or landed
+template <int SC, int C>
+struct RowRaw {
+    RawChunk<C, 3> g;
+    RawChunk<C, SC> s;
+};
+
+template <int SC, int C>
+__device__ __forceinline__ RowRaw<SC, C> prefetch_row(const Args &g, const uint8_t *G, const uint8_t *S, int yy,
+                                                      int gx0, bool fast)
 {
-    float gch[C][3], sch[C][SC];
-    load_chunk<C, 3>(G + (size_t)yy * g.w * 3, gx0, g.w, fast, gch);
-    load_chunk<C, SC>(S + (size_t)yy * g.w * SC, gx0, g.w, fast, sch);
+    RowRaw<SC, C> r;
+    r.g = load_raw<C, 3>(G + (size_t)yy * g.w * 3, gx0, g.w, fast);
+    r.s = load_raw<C, SC>(S + (size_t)yy * g.w * SC, gx0, g.w, fast);
+    return r;
+}
+
+template <int SC, int C, int Q0, int NQ>
+__device__ __forceinline__ void accumulate(float (&V)[NQG][C], const RowRaw<SC, C> &row, float sign)
+{
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         float ch[7];
-        ch[0] = gch[c][0];
-        ch[1] = gch[c][1];
-        ch[2] = gch[c][2];
+        ch[0] = raw_channel<C, 3>(row.g, c, 0);
+        ch[1] = raw_channel<C, 3>(row.g, c, 1);
+        ch[2] = raw_channel<C, 3>(row.g, c, 2);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) ch[3 + k] = k < SC ? sch[c][k] : 0.0f;
+        for (int k = 0; k < 3; ++k) ch[3 + k] = k < SC ? raw_channel<C, SC>(row.s, c, k < SC ? k : 0) : 0.0f;
         ch[6] = 1.0f;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) V[q][c] = fmaf(sign * ch[qa(Q0 + q)], ch[qb(Q0 + q)], V[q][c]);
@@ -188,17 +214,26 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
 #pragma unroll
         for (int c = 0; c < C; ++c) V[q][c] = 0.0f;
 
-    for (int dy = -r; dy < r; ++dy) {
-        const int yy = reflect(y0 + dy, g.h);
-        if (SC == 1) { RF_GF2_GROUPS_1(accumulate, V, g, G, S, yy, gx0, fast, 1.0f) }
-        else { RF_GF2_GROUPS_3(accumulate, V, g, G, S, yy, gx0, fast, 1.0f) }
-    }
-    for (int y = y0; y < y1; ++y) {
-        {
-            const int yy = reflect(y + r, g.h);
-            if (SC == 1) { RF_GF2_GROUPS_1(accumulate, V, g, G, S, yy, gx0, fast, 1.0f) }
-            else { RF_GF2_GROUPS_3(accumulate, V, g, G, S, yy, gx0, fast, 1.0f) }
+#define RF_GF2_ACC(ROW, SIGN)                                                  \
+    if (SC == 1) { RF_GF2_GROUPS_1(accumulate, V, ROW, SIGN) }                 \
+    else { RF_GF2_GROUPS_3(accumulate, V, ROW, SIGN) }
+
+    // warm-up: rows y0-r .. y0+r-1, two rows in flight
+    {
+        RowRaw<SC, C> cur = prefetch_row<SC, C>(g, G, S, reflect(y0 - r, g.h), gx0, fast);
+        for (int dy = -r; dy < r; ++dy) {
+            const RowRaw<SC, C> nxt = prefetch_row<SC, C>(g, G, S, reflect(y0 + dy + 1, g.h), gx0, fast);
+            RF_GF2_ACC(cur, 1.0f)
+            cur = nxt;
         }
+    }
+    // the entering and leaving rows of output row y are requested one whole row of work ahead
+    RowRaw<SC, C> row_in = prefetch_row<SC, C>(g, G, S, reflect(y0 + r, g.h), gx0, fast);
+    RowRaw<SC, C> row_out = prefetch_row<SC, C>(g, G, S, reflect(y0 - r, g.h), gx0, fast);
+    for (int y = y0; y < y1; ++y) {
+        const RowRaw<SC, C> nxt_in = prefetch_row<SC, C>(g, G, S, reflect(y + 1 + r, g.h), gx0, fast);
+        const RowRaw<SC, C> nxt_out = prefetch_row<SC, C>(g, G, S, reflect(y + 1 - r, g.h), gx0, fast);
+        RF_GF2_ACC(row_in, 1.0f)
         uint32_t *P = pbuf + ((y - y0) & 1) * (Q * NX);
         if (SC == 1) { RF_GF2_GROUPS_1(scan_store_sc, V, P, NX, lane) }
         else { RF_GF2_GROUPS_3(scan_store_sc, V, P, NX, lane) }
@@ -263,12 +298,11 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
                 o[3 * img_px] = b;
             }
         }
-        {
-            const int yy = reflect(y - r, g.h);
-            if (SC == 1) { RF_GF2_GROUPS_1(accumulate, V, g, G, S, yy, gx0, fast, -1.0f) }
-            else { RF_GF2_GROUPS_3(accumulate, V, g, G, S, yy, gx0, fast, -1.0f) }
-        }
+        RF_GF2_ACC(row_out, -1.0f)
+        row_in = nxt_in;
+        row_out = nxt_out;
     }
+#undef RF_GF2_ACC
 }
 
 // ---- pass B ---------------------------------------------------------------------------------------
@@ -311,15 +345,32 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
     float V[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) V[c] = 0.0f;
-    auto add_row = [&](int yy, float sign) {
+    struct Chunk {
         float v[C];
-        load_plane_chunk<C>(A + (size_t)yy * g.w, gx0, g.w, fast, v);
-#pragma unroll
-        for (int c = 0; c < C; ++c) V[c] = fmaf(sign, v[c], V[c]);
     };
-    for (int dy = -r; dy < r; ++dy) add_row(reflect(y0 + dy, g.h), 1.0f);
+    auto fetch = [&](int yy) {
+        Chunk k;
+        load_plane_chunk<C>(A + (size_t)yy * g.w, gx0, g.w, fast, k.v);
+        return k;
+    };
+    auto add = [&](const Chunk &k, float sign) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) V[c] = fmaf(sign, k.v[c], V[c]);
+    };
+    {
+        Chunk cur = fetch(reflect(y0 - r, g.h));
+        for (int dy = -r; dy < r; ++dy) {
+            const Chunk nxt = fetch(reflect(y0 + dy + 1, g.h));
+            add(cur, 1.0f);
+            cur = nxt;
+        }
+    }
+    Chunk row_in = fetch(reflect(y0 + r, g.h));
+    Chunk row_out = fetch(reflect(y0 - r, g.h));
     for (int y = y0; y < y1; ++y) {
-        add_row(reflect(y + r, g.h), 1.0f);
+        const Chunk nxt_in = fetch(reflect(y + 1 + r, g.h));
+        const Chunk nxt_out = fetch(reflect(y + 1 - r, g.h));
+        add(row_in, 1.0f);
         float *P = fbuf + ((y - y0) & 1) * (Q * NX);
         {
             float pre[C];
@@ -364,7 +415,9 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
                 o[c] = sat_u8(v);
             }
         }
-        add_row(reflect(y - r, g.h), -1.0f);
+        add(row_out, -1.0f);
+        row_in = nxt_in;
+        row_out = nxt_out;
     }
 }
 
@@ -395,7 +448,8 @@ static Plan make_plan(int n, int h, int w, int r, int sms, int warps_per_cta)
     const long want = (long)sms * 16 / warps_per_cta;  // ~16 resident warps per SM
     if (ctas < want) {
         int segs = (int)((want + ctas - 1) / ctas);
-        const int max_segs = h / (4 * r + 2) > 1 ? h / (4 * r + 2) : 1;  // keep warm-up below ~50 %
+        // a warm-up row costs only its accumulate (about a quarter of a full row), so short segments are fine
+        const int max_segs = h / 64 > 1 ? h / 64 : 1;
         if (segs > max_segs) segs = max_segs;
         best.segs = segs;
         best.seg_rows = (h + segs - 1) / segs;
