@@ -52,6 +52,19 @@ struct RawChunk {
     uint32_t w[C * CN / 4];
 };
 
+// border lanes (chunk partly outside the image): one packed word from reflected byte loads; kept out of
+// line so the unrolled kernels carry a single copy of this rarely taken path
+__device__ __noinline__ uint32_t border_word(const uint8_t *row, int gx0, int w, int cn, int word)
+{
+    uint32_t v = 0;
+    for (int b = 0; b < 4; ++b) {
+        const int byte = word * 4 + b;
+        const int c = byte / cn, k = byte - c * cn;
+        v |= (uint32_t)row[(size_t)reflect(gx0 + c, w) * cn + k] << (8 * b);
+    }
+    return v;
+}
+
 template <int C, int CN>
 __device__ __forceinline__ RawChunk<C, CN> load_raw(const uint8_t *row, int gx0, int w, bool fast)
 {
@@ -62,16 +75,7 @@ __device__ __forceinline__ RawChunk<C, CN> load_raw(const uint8_t *row, int gx0,
         for (int i = 0; i < C * CN / 4; ++i) r.w[i] = __ldg(p + i);
     } else {
 #pragma unroll
-        for (int i = 0; i < C * CN / 4; ++i) r.w[i] = 0u;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const uint8_t *px = row + (size_t)reflect(gx0 + c, w) * CN;
-#pragma unroll
-            for (int k = 0; k < CN; ++k) {
-                const int byte = c * CN + k;
-                r.w[byte >> 2] |= (uint32_t)px[k] << (8 * (byte & 3));
-            }
-        }
+        for (int i = 0; i < C * CN / 4; ++i) r.w[i] = border_word(row, gx0, w, CN, i);
     }
     return r;
 }
@@ -218,22 +222,18 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
     if (SC == 1) { RF_GF2_GROUPS_1(accumulate, V, ROW, SIGN) }                 \
     else { RF_GF2_GROUPS_3(accumulate, V, ROW, SIGN) }
 
-    // warm-up: rows y0-r .. y0+r-1, two rows in flight
-    {
-        RowRaw<SC, C> cur = prefetch_row<SC, C>(g, G, S, reflect(y0 - r, g.h), gx0, fast);
-        for (int dy = -r; dy < r; ++dy) {
-            const RowRaw<SC, C> nxt = prefetch_row<SC, C>(g, G, S, reflect(y0 + dy + 1, g.h), gx0, fast);
-            RF_GF2_ACC(cur, 1.0f)
-            cur = nxt;
-        }
-    }
-    // the entering and leaving rows of output row y are requested one whole row of work ahead
-    RowRaw<SC, C> row_in = prefetch_row<SC, C>(g, G, S, reflect(y0 + r, g.h), gx0, fast);
-    RowRaw<SC, C> row_out = prefetch_row<SC, C>(g, G, S, reflect(y0 - r, g.h), gx0, fast);
-    for (int y = y0; y < y1; ++y) {
-        const RowRaw<SC, C> nxt_in = prefetch_row<SC, C>(g, G, S, reflect(y + 1 + r, g.h), gx0, fast);
+    // One loop over the rows entering the window: steps 0..2r-1 only warm the vertical sums up, every
+    // later step also emits output row y.  Rows are requested one step ahead of their use.
+    RowRaw<SC, C> cur_in = prefetch_row<SC, C>(g, G, S, reflect(y0 - r, g.h), gx0, fast);
+    RowRaw<SC, C> cur_out = prefetch_row<SC, C>(g, G, S, reflect(y0 - r, g.h), gx0, fast);
+    const int n_steps = 2 * r + (y1 - y0);
+    for (int t = 0; t < n_steps; ++t) {
+        const RowRaw<SC, C> nxt_in = prefetch_row<SC, C>(g, G, S, reflect(y0 - r + t + 1, g.h), gx0, fast);
+        RF_GF2_ACC(cur_in, 1.0f)
+        cur_in = nxt_in;
+        if (t < 2 * r) continue;
+        const int y = y0 + t - 2 * r;
         const RowRaw<SC, C> nxt_out = prefetch_row<SC, C>(g, G, S, reflect(y + 1 - r, g.h), gx0, fast);
-        RF_GF2_ACC(row_in, 1.0f)
         uint32_t *P = pbuf + ((y - y0) & 1) * (Q * NX);
         if (SC == 1) { RF_GF2_GROUPS_1(scan_store_sc, V, P, NX, lane) }
         else { RF_GF2_GROUPS_3(scan_store_sc, V, P, NX, lane) }
@@ -298,15 +298,16 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
                 o[3 * img_px] = b;
             }
         }
-        RF_GF2_ACC(row_out, -1.0f)
-        row_in = nxt_in;
-        row_out = nxt_out;
+        RF_GF2_ACC(cur_out, -1.0f)
+        cur_out = nxt_out;
     }
 #undef RF_GF2_ACC
 }
 
 // ---- pass B ---------------------------------------------------------------------------------------
 // one warp per coefficient plane (4 * SC warps); FP32 vertical sliding sums and FP32 prefixes
+__device__ __noinline__ float border_float(const float *row, int gx, int w) { return row[reflect(gx, w)]; }
+
 template <int C>
 __device__ __forceinline__ void load_plane_chunk(const float *row, int gx0, int w, bool fast, float (&v)[C])
 {
@@ -321,7 +322,7 @@ __device__ __forceinline__ void load_plane_chunk(const float *row, int gx0, int 
         }
     } else {
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = row[reflect(gx0 + c, w)];
+        for (int c = 0; c < C; ++c) v[c] = border_float(row, gx0 + c, w);
     }
 }
 
@@ -357,20 +358,16 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
 #pragma unroll
         for (int c = 0; c < C; ++c) V[c] = fmaf(sign, k.v[c], V[c]);
     };
-    {
-        Chunk cur = fetch(reflect(y0 - r, g.h));
-        for (int dy = -r; dy < r; ++dy) {
-            const Chunk nxt = fetch(reflect(y0 + dy + 1, g.h));
-            add(cur, 1.0f);
-            cur = nxt;
-        }
-    }
-    Chunk row_in = fetch(reflect(y0 + r, g.h));
-    Chunk row_out = fetch(reflect(y0 - r, g.h));
-    for (int y = y0; y < y1; ++y) {
-        const Chunk nxt_in = fetch(reflect(y + 1 + r, g.h));
+    Chunk cur_in = fetch(reflect(y0 - r, g.h));
+    Chunk cur_out = fetch(reflect(y0 - r, g.h));
+    const int n_steps = 2 * r + (y1 - y0);
+    for (int t = 0; t < n_steps; ++t) {
+        const Chunk nxt_in = fetch(reflect(y0 - r + t + 1, g.h));
+        add(cur_in, 1.0f);
+        cur_in = nxt_in;
+        if (t < 2 * r) continue;
+        const int y = y0 + t - 2 * r;
         const Chunk nxt_out = fetch(reflect(y + 1 - r, g.h));
-        add(row_in, 1.0f);
         float *P = fbuf + ((y - y0) & 1) * (Q * NX);
         {
             float pre[C];
@@ -415,9 +412,8 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
                 o[c] = sat_u8(v);
             }
         }
-        add(row_out, -1.0f);
-        row_in = nxt_in;
-        row_out = nxt_out;
+        add(cur_out, -1.0f);
+        cur_out = nxt_out;
     }
 }
 
