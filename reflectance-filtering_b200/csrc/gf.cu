@@ -314,22 +314,32 @@ static int run(Args a, cudaStream_t st)
 
 namespace rf {
 namespace gf2 {  // gf2.cu: strip kernels for radius <= 64
-bool supported(int r);
-int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, float *ab, int n, int h, int w, int r,
+bool supported(int r, int h, int w);
+size_t workspace_per_image(int sc, int h, int w, int r);
+int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws, int n, int h, int w, int r,
         double eps, cudaStream_t st);
 }  // namespace gf2
 }  // namespace rf
 
 using namespace rf;
 
+static size_t per_image_bytes(int sc, int h, int w, int radius)
+{
+    size_t per = gf::per_image_ws(sc, h, w);
+    if (gf2::supported(radius, h, w)) {
+        const size_t p2 = gf2::workspace_per_image(sc, h, w, radius);
+        if (p2 > per) per = p2;
+    }
+    return per;
+}
+
 extern "C" int rf_guided_max_radius(void) { return gf::MAX_RADIUS; }
 
 extern "C" size_t rf_guided_workspace_bytes(int sc, int n, int h, int w, int radius)
 {
-    (void)radius;
     if (!(sc == 1 || sc == 3) || n < 1 || h < 1 || w < 1) return 0;
     // the call processes the batch in chunks if given less; never ask for more than 8 GiB
-    const size_t per = gf::per_image_ws(sc, h, w);
+    const size_t per = per_image_bytes(sc, h, w, radius);
     size_t want = per * (size_t)n;
     const size_t cap = (size_t)8 << 30;
     if (want > cap) want = (cap / per > 0 ? cap / per : 1) * per;
@@ -360,19 +370,19 @@ extern "C" int rf_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, in
         return fail(RF_EUNSUPPORTED, "rf_guided_u8: radius %d exceeds the supported maximum %d", radius, gf::MAX_RADIUS);
     if (n == 0) return RF_OK;
     if (dst == src || dst == guide) return fail(RF_EINVAL, "rf_guided_u8: dst must not alias an input");
-    const size_t per = gf::per_image_ws(sc, h, w);
+    const size_t per = per_image_bytes(sc, h, w, radius);
     if (ws_bytes < per) return fail(RF_EINVAL, "rf_guided_u8: workspace too small (%zu < %zu bytes)", ws_bytes, per);
     if ((uintptr_t)ws % 16) return fail(RF_EINVAL, "rf_guided_u8: workspace must be 16-byte aligned");
     const int k = 2 * radius + 1;
     int chunk = (int)(ws_bytes / per < (size_t)n ? ws_bytes / per : (size_t)n);
     if (chunk > 65535) chunk = 65535;
     const size_t img_px = (size_t)h * w;
-    const bool generic = !gf2::supported(radius) || (flags_generic_path() != 0);
+    const bool generic = !gf2::supported(radius, h, w) || (flags_generic_path() != 0);
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int nn = n - i0 < chunk ? n - i0 : chunk;
         if (!generic) {
-            int rc = gf2::run(guide + i0 * img_px * 3, src + i0 * img_px * sc, sc, dst + i0 * img_px * sc, (float *)ws,
-                              nn, h, w, radius, eps, (cudaStream_t)stream);
+            int rc = gf2::run(guide + i0 * img_px * 3, src + i0 * img_px * sc, sc, dst + i0 * img_px * sc, ws, nn, h, w,
+                              radius, eps, (cudaStream_t)stream);
             if (rc != RF_OK) return rc;
             continue;
         }

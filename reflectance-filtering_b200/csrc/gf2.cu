@@ -1,22 +1,26 @@
-// Guided filter, fast path for radius <= 64: strip kernels with per-lane column chunks.
+// Guided filter, fast path for radius <= 64 (and images at least one halo wide): strip kernels with
+// per-lane column chunks over column-padded planes.
 //
 // Same semantics as gf.cu (ximgproc guidedFilter; call site
-// /root/reference/filter_reflectance.py:67-70).  What changes is the work decomposition, chosen from
-// the measured pipe rates on B200 (profiles/r01_microbench_pipes.txt): SHFL, I2F and anything FP64 issue
-// at 1/4 to 1/8 of the FP32 rate, so
+// /root/reference/filter_reflectance.py:67-70).  The work decomposition follows the measured pipe rates
+// on B200 (profiles/r01_microbench_pipes.txt): SHFL, I2F and anything FP64 issue at 1/4 to 1/8 of the FP32
+// rate, byte loads with per-pixel border logic are poison, so
+//   * a pack kernel writes guide + source once as 32-bit pixels (B | G<<8 | R<<16 | p<<24) into planes
+//     that are padded by the halo with BORDER_REFLECT columns already resolved: every later load is an
+//     aligned 128-bit load of four pixels, with no border case in x (rows reflect by index);
 //   * every lane owns C consecutive columns of a 32*C wide strip and keeps the vertical window sums of
-//     its quantities in FP32 registers -- they are integers below 2^23 ((2r+1)*255^2 for r <= 64), so
-//     the FFMA updates (add the entering row, subtract the leaving one) are exact;
-//   * the horizontal direction is a per-lane serial prefix over its C columns plus ONE 5-step warp
-//     scan of the lane totals per quantity (uint32, wrap-around safe): 5/C shuffles per column;
-//   * the quantities are split over the warps of the CTA (each warp scans the whole strip width for
+//     its quantities in FP32 registers -- integers below 2^23 ((2r+1)*255^2 for r <= 64), so the FFMA
+//     updates (add the entering row, subtract the leaving one) are exact;
+//   * the horizontal direction is a per-lane serial prefix over its C columns plus ONE 5-step warp scan
+//     of the lane totals per quantity (uint32, wrap-around safe): 5/C shuffles per column;
+//   * the 9 + 4*SC quantities are split over the warps of the CTA (each warp scans the whole strip for
 //     its 3-4 quantities); prefixes go to a double-buffered shared-memory row, and after ONE
 //     __syncthreads per row all threads turn P[x+r] - P[x-r-1] into means, solve the 3x3 system with
-//     the oracle's non-contracted multiply/add order and store the coefficient planes;
+//     the oracle's non-contracted multiply/add order and store the coefficient planes (again padded,
+//     border pixels mirrored into the halo so pass B has no border case either);
 //   * no FP64: the box mean is float(S) * float(1/k^2) (<= 1 ulp from OpenCV's float(double(S)/k^2);
 //     measured effect ~2.5e-5 of the output bytes move by 1 LSB); pass B accumulates the
 //     coefficient planes in FP32 the same way.
-// Coefficient planes are planar: ab[n][SC][4][h][w] = (a0, a1, a2, b).
 #include "common.cuh"
 
 namespace rf {
@@ -28,15 +32,16 @@ constexpr int QMAX = 21;
 struct Args {
     const uint8_t *guide;  // [n][h][w][3]
     const uint8_t *src;    // [n][h][w][SC]
-    float *ab;             // [n][SC][4][h][w]
+    uint32_t *packed;      // [n][NP][h][wp]  NP = 1 (SC == 1: B,G,R,p) or 2 (SC == 3: B,G,R,0 / p0,p1,p2,0)
+    float *ab;             // [n][SC][4][h][wp]  (a0, a1, a2, b), columns padded like `packed`
     uint8_t *dst;          // [n][h][w][SC]
     int n, h, w, r;
-    int rh;          // halo columns on each side of a strip: round_up(r + 1, 4)
+    int rh;          // halo columns on each side: round_up(r + 1, 4)
+    int wp;          // padded row pitch in pixels: round_up(w + 2 * rh + 16, 4)
     int twe;         // output columns per strip (multiple of 4)
     int seg_rows;    // output rows per CTA
     float eps;
     float inv_area;  // 1 / (2r+1)^2
-    int fast_loads;  // w % 4 == 0 and 16-byte aligned base pointers: 32-bit loads of pixel chunks
 };
 
 __device__ __forceinline__ float b2f(uint32_t word, int byte)
@@ -44,47 +49,28 @@ __device__ __forceinline__ float b2f(uint32_t word, int byte)
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u | (uint32_t)byte)) - 8388608.0f;
 }
 
-// Raw bytes of the C pixels [gx0, gx0 + C) of one image row, packed into 32-bit words in memory order
-// (byte j of the chunk is byte j & 3 of word j >> 2).  Fast path: chunk inside the image and 4-byte
-// aligned -> plain 32-bit loads; border lanes assemble the same words from reflected byte loads.
-template <int C, int CN>
-struct RawChunk {
-    uint32_t w[C * CN / 4];
-};
-
-// border lanes (chunk partly outside the image): one packed word from reflected byte loads; kept out of
-// line so the unrolled kernels carry a single copy of this rarely taken path
-__device__ __noinline__ uint32_t border_word(const uint8_t *row, int gx0, int w, int cn, int word)
+// ---- pack: u8 interleaved -> padded 32-bit pixels ------------------------------------------------
+template <int SC>
+__global__ void pack_kernel(const Args g)
 {
-    uint32_t v = 0;
-    for (int b = 0; b < 4; ++b) {
-        const int byte = word * 4 + b;
-        const int c = byte / cn, k = byte - c * cn;
-        v |= (uint32_t)row[(size_t)reflect(gx0 + c, w) * cn + k] << (8 * b);
-    }
-    return v;
-}
-
-template <int C, int CN>
-__device__ __forceinline__ RawChunk<C, CN> load_raw(const uint8_t *row, int gx0, int w, bool fast)
-{
-    RawChunk<C, CN> r;
-    if (fast && gx0 >= 0 && gx0 + C <= w) {
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)gx0 * CN);
-#pragma unroll
-        for (int i = 0; i < C * CN / 4; ++i) r.w[i] = __ldg(p + i);
+    const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int img = blockIdx.z;
+    if (xp >= g.wp) return;
+    const int x = reflect(xp - g.rh, g.w);
+    const size_t img_px = (size_t)g.h * g.w;
+    const uint8_t *gp = g.guide + (img * img_px + (size_t)y * g.w + x) * 3;
+    const uint8_t *sp = g.src + (img * img_px + (size_t)y * g.w + x) * SC;
+    const uint32_t bgr = gp[0] | ((uint32_t)gp[1] << 8) | ((uint32_t)gp[2] << 16);
+    const size_t plane = (size_t)g.h * g.wp;
+    constexpr int NP = SC == 1 ? 1 : 2;
+    uint32_t *o = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp + xp;
+    if (SC == 1) {
+        o[0] = bgr | ((uint32_t)sp[0] << 24);
     } else {
-#pragma unroll
-        for (int i = 0; i < C * CN / 4; ++i) r.w[i] = border_word(row, gx0, w, CN, i);
+        o[0] = bgr;
+        o[plane] = sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16);
     }
-    return r;
-}
-
-template <int C, int CN>
-__device__ __forceinline__ float raw_channel(const RawChunk<C, CN> &r, int c, int k)
-{
-    const int byte = c * CN + k;
-    return b2f(r.w[byte >> 2], byte & 3);
 }
 
 // channel ids: 0..2 guide, 3..5 source, 6 = the constant 1.  Quantity q is ch[qa(q)] * ch[qb(q)].
@@ -103,20 +89,39 @@ __host__ __device__ constexpr bool q_is_linear(int q) { return qb(q) == 6; }
 
 constexpr int NQG = 4;  // most quantities any warp owns
 
-// one image row's guide + source chunk of this lane, in flight or landed
+// one padded row's chunk of this lane (C packed pixels per plane), in flight or landed
 template <int SC, int C>
 struct RowRaw {
-    RawChunk<C, 3> g;
-    RawChunk<C, SC> s;
+    uint32_t w0[C];
+    uint32_t w1[SC == 1 ? 1 : C];
 };
 
 template <int SC, int C>
-__device__ __forceinline__ RowRaw<SC, C> prefetch_row(const Args &g, const uint8_t *G, const uint8_t *S, int yy,
-                                                      int gx0, bool fast)
+__device__ __forceinline__ RowRaw<SC, C> prefetch_row(const uint32_t *plane0, size_t plane_stride, int wp, int yy, int xp0)
 {
     RowRaw<SC, C> r;
-    r.g = load_raw<C, 3>(G + (size_t)yy * g.w * 3, gx0, g.w, fast);
-    r.s = load_raw<C, SC>(S + (size_t)yy * g.w * SC, gx0, g.w, fast);
+    const uint4 *p = reinterpret_cast<const uint4 *>(plane0 + (size_t)yy * wp + xp0);
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+        const uint4 t = __ldg(p + c / 4);
+        r.w0[c] = t.x;
+        r.w0[c + 1] = t.y;
+        r.w0[c + 2] = t.z;
+        r.w0[c + 3] = t.w;
+    }
+    if (SC == 3) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(plane0 + plane_stride + (size_t)yy * wp + xp0);
+#pragma unroll
+        for (int c = 0; c < (SC == 1 ? 0 : C); c += 4) {
+            const uint4 t = __ldg(q + c / 4);
+            r.w1[c] = t.x;
+            r.w1[c + 1] = t.y;
+            r.w1[c + 2] = t.z;
+            r.w1[c + 3] = t.w;
+        }
+    } else {
+        r.w1[0] = 0u;
+    }
     return r;
 }
 
@@ -126,11 +131,18 @@ __device__ __forceinline__ void accumulate(float (&V)[NQG][C], const RowRaw<SC, 
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         float ch[7];
-        ch[0] = raw_channel<C, 3>(row.g, c, 0);
-        ch[1] = raw_channel<C, 3>(row.g, c, 1);
-        ch[2] = raw_channel<C, 3>(row.g, c, 2);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ch[3 + k] = k < SC ? raw_channel<C, SC>(row.s, c, k < SC ? k : 0) : 0.0f;
+        ch[0] = b2f(row.w0[c], 0);
+        ch[1] = b2f(row.w0[c], 1);
+        ch[2] = b2f(row.w0[c], 2);
+        if (SC == 1) {
+            ch[3] = b2f(row.w0[c], 3);
+            ch[4] = 0.0f;
+            ch[5] = 0.0f;
+        } else {
+            ch[3] = b2f(row.w1[SC == 1 ? 0 : c], 0);
+            ch[4] = b2f(row.w1[SC == 1 ? 0 : c], 1);
+            ch[5] = b2f(row.w1[SC == 1 ? 0 : c], 2);
+        }
         ch[6] = 1.0f;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) V[q][c] = fmaf(sign * ch[qa(Q0 + q)], ch[qb(Q0 + q)], V[q][c]);
@@ -138,7 +150,7 @@ __device__ __forceinline__ void accumulate(float (&V)[NQG][C], const RowRaw<SC, 
 }
 
 // per-lane serial prefix + warp scan of the lane totals; inclusive strip-wide prefixes to shared memory
-template <int C, int Q0, int NQ>
+template <int SC, int C, int Q0, int NQ>
 __device__ __forceinline__ void scan_store(const float (&V)[NQG][C], uint32_t *P, int nx, int lane)
 {
 #pragma unroll
@@ -165,29 +177,25 @@ __device__ __forceinline__ void scan_store(const float (&V)[NQG][C], uint32_t *P
     }
 }
 
-// warp-uniform dispatch of the per-group templates
-#define RF_GF2_GROUPS_1(FN, ...)                          \
-    switch (group) {                                      \
-        case 0: FN<SC, C, 0, 3>(__VA_ARGS__); break;      \
-        case 1: FN<SC, C, 3, 3>(__VA_ARGS__); break;      \
-        case 2: FN<SC, C, 6, 3>(__VA_ARGS__); break;      \
-        default: FN<SC, C, 9, 4>(__VA_ARGS__); break;     \
+// warp-uniform dispatch of the per-group templates (gray: 4 warps, colour source: 6 warps)
+#define RF_GF2_DISPATCH(FN, ...)                              \
+    if (SC == 1) {                                            \
+        switch (group) {                                      \
+            case 0: FN<SC, C, 0, 3>(__VA_ARGS__); break;      \
+            case 1: FN<SC, C, 3, 3>(__VA_ARGS__); break;      \
+            case 2: FN<SC, C, 6, 3>(__VA_ARGS__); break;      \
+            default: FN<SC, C, 9, 4>(__VA_ARGS__); break;     \
+        }                                                     \
+    } else {                                                  \
+        switch (group) {                                      \
+            case 0: FN<SC, C, 0, 3>(__VA_ARGS__); break;      \
+            case 1: FN<SC, C, 3, 3>(__VA_ARGS__); break;      \
+            case 2: FN<SC, C, 6, 3>(__VA_ARGS__); break;      \
+            case 3: FN<SC, C, 9, 4>(__VA_ARGS__); break;      \
+            case 4: FN<SC, C, 13, 4>(__VA_ARGS__); break;     \
+            default: FN<SC, C, 17, 4>(__VA_ARGS__); break;    \
+        }                                                     \
     }
-#define RF_GF2_GROUPS_3(FN, ...)                          \
-    switch (group) {                                      \
-        case 0: FN<SC, C, 0, 3>(__VA_ARGS__); break;      \
-        case 1: FN<SC, C, 3, 3>(__VA_ARGS__); break;      \
-        case 2: FN<SC, C, 6, 3>(__VA_ARGS__); break;      \
-        case 3: FN<SC, C, 9, 4>(__VA_ARGS__); break;      \
-        case 4: FN<SC, C, 13, 4>(__VA_ARGS__); break;     \
-        default: FN<SC, C, 17, 4>(__VA_ARGS__); break;    \
-    }
-
-template <int SC, int C, int Q0, int NQ>
-__device__ __forceinline__ void scan_store_sc(const float (&V)[NQG][C], uint32_t *P, int nx, int lane)
-{
-    scan_store<C, Q0, NQ>(V, P, nx, lane);
-}
 
 template <int SC>
 __host__ __device__ constexpr int n_groups() { return SC == 1 ? 4 : 6; }
@@ -196,21 +204,22 @@ __host__ __device__ constexpr int n_groups() { return SC == 1 ? 4 : 6; }
 template <int SC, int C>
 __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args g)
 {
-    constexpr int Q = 9 + 4 * SC, NX = 32 * C, NT = 32 * n_groups<SC>();
+    constexpr int Q = 9 + 4 * SC, NX = 32 * C, NT = 32 * n_groups<SC>(), NP = SC == 1 ? 1 : 2;
     extern __shared__ __align__(16) uint32_t pbuf[];  // [2][Q][NX]
     const int tid = threadIdx.x, lane = tid & 31, group = tid >> 5;
     const int img = blockIdx.z;
-    const int sx0 = blockIdx.x * g.twe;
+    const int sx0 = blockIdx.x * g.twe;  // first output column of the strip (image coordinates)
     const int y0 = blockIdx.y * g.seg_rows;
     const int y1 = min(g.h, y0 + g.seg_rows);
-    const int gx0 = sx0 - g.rh + lane * C;
-    const bool fast = g.fast_loads != 0;
-    const size_t img_px = (size_t)g.h * g.w;
-    const uint8_t *G = g.guide + img * img_px * 3;
-    const uint8_t *S = g.src + img * img_px * SC;
+    const size_t plane = (size_t)g.h * g.wp;
+    const uint32_t *PK = g.packed + (size_t)img * NP * plane;
     const int r = g.r;
     const int n_out = min(g.twe, g.w - sx0);
     const uint32_t bias = (uint32_t)(2 * r + 1) * 0x4B000000u;  // what the biased elements add to a window
+    // padded coordinate of this lane's first column is sx0 + lane*C (strip origin sx0 - rh, plus the rh
+    // offset of the padding).  Lanes whose chunk would start beyond the padded row re-read the last
+    // chunk: their prefixes lie right of every window of this strip and are never used.
+    const int xp0c = min(sx0 + lane * C, g.wp - C);
 
     float V[NQG][C];
 #pragma unroll
@@ -218,25 +227,20 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
 #pragma unroll
         for (int c = 0; c < C; ++c) V[q][c] = 0.0f;
 
-#define RF_GF2_ACC(ROW, SIGN)                                                  \
-    if (SC == 1) { RF_GF2_GROUPS_1(accumulate, V, ROW, SIGN) }                 \
-    else { RF_GF2_GROUPS_3(accumulate, V, ROW, SIGN) }
-
     // One loop over the rows entering the window: steps 0..2r-1 only warm the vertical sums up, every
     // later step also emits output row y.  Rows are requested one step ahead of their use.
-    RowRaw<SC, C> cur_in = prefetch_row<SC, C>(g, G, S, reflect(y0 - r, g.h), gx0, fast);
-    RowRaw<SC, C> cur_out = prefetch_row<SC, C>(g, G, S, reflect(y0 - r, g.h), gx0, fast);
+    RowRaw<SC, C> cur_in = prefetch_row<SC, C>(PK, plane, g.wp, reflect(y0 - r, g.h), xp0c);
+    RowRaw<SC, C> cur_out = cur_in;
     const int n_steps = 2 * r + (y1 - y0);
     for (int t = 0; t < n_steps; ++t) {
-        const RowRaw<SC, C> nxt_in = prefetch_row<SC, C>(g, G, S, reflect(y0 - r + t + 1, g.h), gx0, fast);
-        RF_GF2_ACC(cur_in, 1.0f)
+        const RowRaw<SC, C> nxt_in = prefetch_row<SC, C>(PK, plane, g.wp, reflect(y0 - r + t + 1, g.h), xp0c);
+        RF_GF2_DISPATCH(accumulate, V, cur_in, 1.0f)
         cur_in = nxt_in;
         if (t < 2 * r) continue;
         const int y = y0 + t - 2 * r;
-        const RowRaw<SC, C> nxt_out = prefetch_row<SC, C>(g, G, S, reflect(y + 1 - r, g.h), gx0, fast);
+        const RowRaw<SC, C> nxt_out = prefetch_row<SC, C>(PK, plane, g.wp, reflect(y + 1 - r, g.h), xp0c);
         uint32_t *P = pbuf + ((y - y0) & 1) * (Q * NX);
-        if (SC == 1) { RF_GF2_GROUPS_1(scan_store_sc, V, P, NX, lane) }
-        else { RF_GF2_GROUPS_3(scan_store_sc, V, P, NX, lane) }
+        RF_GF2_DISPATCH(scan_store, V, P, NX, lane)
         // One barrier per row: prefixes of row y are visible, and every thread has finished the math of
         // row y-1 (so the buffer written two rows from now is free).
         __syncthreads();
@@ -272,7 +276,10 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
             const float rdet = __frcp_rn(det);
             const float i00 = __fmul_rn(f00, rdet), i01 = __fmul_rn(f01, rdet), i02 = __fmul_rn(f02, rdet);
             const float i11 = __fmul_rn(f11, rdet), i12 = __fmul_rn(f12, rdet), i22 = __fmul_rn(f22, rdet);
-            const size_t opix = (size_t)y * g.w + sx0 + idx;
+            const int x = sx0 + idx;
+            // mirrored copies for the halo columns pass B will read (BORDER_REFLECT: -1-j <-> j)
+            const int xl = x < g.rh ? g.rh - 1 - x : -1;                   // padded column of the left mirror
+            const int xr = x >= g.w - g.rh ? g.rh + 2 * g.w - 1 - x : -1;  // padded column of the right mirror
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
                 const float mp = m[9 + 4 * c];
@@ -291,55 +298,38 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
                 float b = __fsub_rn(mp, __fmul_rn(a0, m[0]));
                 b = __fsub_rn(b, __fmul_rn(a1, m[1]));
                 b = __fsub_rn(b, __fmul_rn(a2, m[2]));
-                float *o = g.ab + ((size_t)(img * SC + c) * 4) * img_px + opix;
-                o[0] = a0;
-                o[img_px] = a1;
-                o[2 * img_px] = a2;
-                o[3 * img_px] = b;
+                float *o = g.ab + ((size_t)(img * SC + c) * 4) * plane + (size_t)y * g.wp;
+                const float v[4] = {a0, a1, a2, b};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    o[k * plane + g.rh + x] = v[k];
+                    if (xl >= 0) o[k * plane + xl] = v[k];
+                    if (xr >= 0 && xr < g.wp) o[k * plane + xr] = v[k];
+                }
             }
         }
-        RF_GF2_ACC(cur_out, -1.0f)
+        RF_GF2_DISPATCH(accumulate, V, cur_out, -1.0f)
         cur_out = nxt_out;
     }
-#undef RF_GF2_ACC
 }
 
 // ---- pass B ---------------------------------------------------------------------------------------
 // one warp per coefficient plane (4 * SC warps); FP32 vertical sliding sums and FP32 prefixes
-__device__ __noinline__ float border_float(const float *row, int gx, int w) { return row[reflect(gx, w)]; }
-
-template <int C>
-__device__ __forceinline__ void load_plane_chunk(const float *row, int gx0, int w, bool fast, float (&v)[C])
-{
-    if (fast && gx0 >= 0 && gx0 + C <= w) {
-#pragma unroll
-        for (int c = 0; c < C; c += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(row + gx0 + c));
-            v[c] = t.x;
-            v[c + 1] = t.y;
-            v[c + 2] = t.z;
-            v[c + 3] = t.w;
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = border_float(row, gx0 + c, w);
-    }
-}
-
 template <int SC, int C>
 __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
 {
-    constexpr int Q = 4 * SC, NX = 32 * C, NT = 32 * Q;
+    constexpr int Q = 4 * SC, NX = 32 * C, NT = 32 * Q, NP = SC == 1 ? 1 : 2;
     extern __shared__ __align__(16) float fbuf[];  // [2][Q][NX]
-    const int tid = threadIdx.x, lane = tid & 31, plane = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, pl = tid >> 5;
     const int img = blockIdx.z;
     const int sx0 = blockIdx.x * g.twe;
     const int y0 = blockIdx.y * g.seg_rows;
     const int y1 = min(g.h, y0 + g.seg_rows);
-    const int gx0 = sx0 - g.rh + lane * C;
-    const bool fast = g.fast_loads != 0;
+    const int xp0c = min(sx0 + lane * C, g.wp - C);
+    const size_t plane = (size_t)g.h * g.wp;
     const size_t img_px = (size_t)g.h * g.w;
-    const float *A = g.ab + ((size_t)img * Q + plane) * img_px;
+    const float *A = g.ab + ((size_t)img * Q + pl) * plane;
+    const uint32_t *PK = g.packed + (size_t)img * NP * plane;
     const int r = g.r;
     const int n_out = min(g.twe, g.w - sx0);
 
@@ -351,7 +341,15 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
     };
     auto fetch = [&](int yy) {
         Chunk k;
-        load_plane_chunk<C>(A + (size_t)yy * g.w, gx0, g.w, fast, k.v);
+        const float4 *p = reinterpret_cast<const float4 *>(A + (size_t)yy * g.wp + xp0c);
+#pragma unroll
+        for (int c = 0; c < C; c += 4) {
+            const float4 t = __ldg(p + c / 4);
+            k.v[c] = t.x;
+            k.v[c + 1] = t.y;
+            k.v[c + 2] = t.z;
+            k.v[c + 3] = t.w;
+        }
         return k;
     };
     auto add = [&](const Chunk &k, float sign) {
@@ -359,7 +357,7 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
         for (int c = 0; c < C; ++c) V[c] = fmaf(sign, k.v[c], V[c]);
     };
     Chunk cur_in = fetch(reflect(y0 - r, g.h));
-    Chunk cur_out = fetch(reflect(y0 - r, g.h));
+    Chunk cur_out = cur_in;
     const int n_steps = 2 * r + (y1 - y0);
     for (int t = 0; t < n_steps; ++t) {
         const Chunk nxt_in = fetch(reflect(y0 - r + t + 1, g.h));
@@ -380,23 +378,23 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
             float incl = run;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const float t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
+                const float tt = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += tt;
             }
             const float excl = incl - run;
-            float *dst = P + plane * NX + lane * C;
+            float *dstp = P + pl * NX + lane * C;
 #pragma unroll
             for (int c = 0; c < C; c += 4)
-                *reinterpret_cast<float4 *>(dst + c) =
+                *reinterpret_cast<float4 *>(dstp + c) =
                     make_float4(pre[c] + excl, pre[c + 1] + excl, pre[c + 2] + excl, pre[c + 3] + excl);
         }
         __syncthreads();
         for (int idx = tid; idx < n_out; idx += NT) {
             const int i = g.rh + idx;
-            const size_t opix = (size_t)y * g.w + sx0 + idx;
-            const uint8_t *gp = g.guide + (img * img_px + opix) * 3;
-            const float i0 = gp[0], i1 = gp[1], i2 = gp[2];
-            uint8_t *o = g.dst + (img * img_px + opix) * SC;
+            const int x = sx0 + idx;
+            const uint32_t gw = PK[(size_t)y * g.wp + g.rh + x];
+            const float i0 = b2f(gw, 0), i1 = b2f(gw, 1), i2 = b2f(gw, 2);
+            uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + x) * SC;
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
                 float m[4];
@@ -419,14 +417,18 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
 
 // ---- host -------------------------------------------------------------------------------------------
 struct Plan {
-    int C, strips, twe, rh, segs, seg_rows;
+    int C, strips, twe, rh, wp, segs, seg_rows;
 };
+
+static int halo(int r) { return (r + 1 + 3) & ~3; }
+// + 16: the chunk (<= 16 columns) that holds the right-most needed column must lie inside the row
+static int pitch(int w, int r) { return (w + 2 * halo(r) + 16 + 3) & ~3; }
 
 static Plan make_plan(int n, int h, int w, int r, int sms, int warps_per_cta)
 {
     Plan best{};
     long best_cost = -1;
-    const int rh = (r + 1 + 3) & ~3;
+    const int rh = halo(r);
     for (int C : {8, 12, 16}) {
         const int tw = 32 * C - 2 * rh;
         if (tw < 32) continue;
@@ -436,15 +438,15 @@ static Plan make_plan(int n, int h, int w, int r, int sms, int warps_per_cta)
         const long cost = (long)strips * 32 * C;  // columns touched per image row
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
-            best = Plan{C, strips, twe, rh, 1, h};
+            best = Plan{C, strips, twe, rh, pitch(w, r), 1, h};
         }
     }
-    // split rows when the grid cannot fill the SMs; every segment pays 2r rows of warm-up
+    // split rows when the grid cannot fill the SMs; a warm-up row costs only its accumulate (about a
+    // quarter of a full row), so fairly short segments are fine
     const long ctas = (long)best.strips * n;
     const long want = (long)sms * 16 / warps_per_cta;  // ~16 resident warps per SM
     if (ctas < want) {
         int segs = (int)((want + ctas - 1) / ctas);
-        // a warm-up row costs only its accumulate (about a quarter of a full row), so short segments are fine
         const int max_segs = h / 64 > 1 ? h / 64 : 1;
         if (segs > max_segs) segs = max_segs;
         best.segs = segs;
@@ -467,6 +469,9 @@ static int launch(Args a, const Plan &p, cudaStream_t st)
         RF_CUDA_TRY(cudaFuncSetAttribute(pass_b_kernel<SC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured[dev & 63] = true;
     }
+    dim3 pgrid((a.wp + 255) / 256, a.h, a.n);
+    pack_kernel<SC><<<pgrid, 256, 0, st>>>(a);
+    RF_LAUNCH_CHECK("gf2::pack_kernel");
     dim3 grid(p.strips, (a.h + p.seg_rows - 1) / p.seg_rows, a.n);
     pass_a_kernel<SC, C><<<grid, 32 * n_groups<SC>(), smem_a, st>>>(a);
     RF_LAUNCH_CHECK("gf2::pass_a_kernel");
@@ -475,15 +480,21 @@ static int launch(Args a, const Plan &p, cudaStream_t st)
     return RF_OK;
 }
 
-bool supported(int r) { return r >= 1 && r <= MAX_RADIUS; }
+// single reflection must cover the halo, the exact-integer FP32 sums need r <= 64
+bool supported(int r, int h, int w) { return r >= 1 && r <= MAX_RADIUS && w >= halo(r) && h <= 65535; }
 
-int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, float *ab, int n, int h, int w, int r,
+size_t workspace_per_image(int sc, int h, int w, int r)
+{
+    const size_t plane = (size_t)h * pitch(w, r);
+    return plane * 4 * (sc == 1 ? 1 : 2) + plane * 4 * 4 * sc;
+}
+
+int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws, int n, int h, int w, int r,
         double eps, cudaStream_t st)
 {
     Args a;
     a.guide = guide;
     a.src = src;
-    a.ab = ab;
     a.dst = dst;
     a.n = n;
     a.h = h;
@@ -492,12 +503,14 @@ int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, float *a
     a.eps = (float)eps;
     const int k = 2 * r + 1;
     a.inv_area = (float)(1.0 / ((double)k * k));
-    a.fast_loads = (w % 4 == 0) && ((uintptr_t)guide % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
-                   ((uintptr_t)ab % 16 == 0);
     const Plan p = make_plan(n, h, w, r, sm_count(), sc == 1 ? 4 : 6);
     a.rh = p.rh;
+    a.wp = p.wp;
     a.twe = p.twe;
     a.seg_rows = p.seg_rows;
+    const size_t plane = (size_t)h * p.wp;
+    a.packed = (uint32_t *)ws;
+    a.ab = (float *)((uint32_t *)ws + (size_t)n * (sc == 1 ? 1 : 2) * plane);
 #define RF_GF2_LAUNCH(SC_)                                       \
     switch (p.C) {                                               \
         case 8: return launch<SC_, 8>(a, p, st);                 \
