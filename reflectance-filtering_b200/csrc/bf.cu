@@ -18,6 +18,7 @@
 // A second instantiation handles the BF(CNN, CNN) case, where joint and src are gray planes that
 // stand for three equal channels: alpha = 3|dJ|, one channel to accumulate.
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -386,7 +387,25 @@ static int pick_wy(const Args &a, const Geometry &g, bool sep)
 }  // namespace bf
 }  // namespace rf
 
+namespace rf {
+namespace bf2 {  // bf2.cu: packed two-output kernel for single-channel joint + src
+int run(const uint8_t *joint, const uint8_t *src, uint8_t *dst, int n, int h, int w, int r, double sigma_color,
+        double sigma_space, double alpha_scale, cudaStream_t st);
+}
+}  // namespace rf
+
 using namespace rf;
+
+// RF_BF_V1=1 keeps the first-generation gray kernel (used to cross-check the two implementations)
+static bool use_v1_gray()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RF_BF_V1");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 extern "C" int rf_joint_bilateral_max_radius(void) { return bf::MAX_RADIUS; }
 
@@ -441,6 +460,9 @@ extern "C" int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t
     cudaStream_t st = (cudaStream_t)stream;
     const double ksq = std::sqrt(0.5 / (sigma_color * sigma_color) * 1.4426950408889634074);
     const bool gray = (jc == 1 && sc == 1);
+    if (gray && !use_v1_gray())
+        return bf2::run(joint, src, dst, n, h, w, g.r, sigma_color, sigma_space, gray_rep ? 3.0 : 1.0,
+                        (cudaStream_t)stream);
     if (gray) {
         const double scale = gray_rep ? 3.0 : 1.0;
         a.ksqrt = (float)(ksq * scale);

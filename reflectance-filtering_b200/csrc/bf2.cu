@@ -1,0 +1,298 @@
+// Joint bilateral filter, single-channel (gray) path, second generation.
+//
+// Same semantics as bf.cu (jointBilateralFilter_8u; call site
+// /root/reference/filter_reflectance.py:60-64) for the case where joint and src are one plane each:
+// the BF(CNN, CNN) configuration (alpha = 3|dJ| for the three equal channels cv2.imread makes of the
+// CNN's gray PNG) and true 1-channel images (alpha = |dJ|).
+//
+// What ncu showed for the first kernel (profiles/r01_bf_gray_v1_ncu_full.txt): the XU pipe (MUFU.EX2, one
+// per tap, 16 lanes/clk/SM) is 86 % busy, but 15.5 % of the executed taps lie outside the disc because a
+// thread's 8 outputs x 4 neighbours form a coarse block.  This version makes the block 2 x 2:
+//   * a thread owns TWO adjacent outputs, held as the halves of 64-bit registers; every FP32 step of a tap
+//     pair is one packed instruction (FFMA2 / FMUL2 / FADD2 issue at half rate but carry two taps), so the
+//     issue slots per tap drop from 6.3 to ~4.9 and leave the XU pipe as the only limiter;
+//   * neighbours arrive two at a time (LDS.64), executed taps / useful taps = 1.035 instead of 1.18;
+//   * the per-row spatial exponents for the four taps of a chunk come from one broadcast LDS.128 of a
+//     table laid out per chunk: (e(qb), e(qb-1), e(qb+1), e(qb)), +inf outside the disc (weight 0).
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rf {
+namespace bf2 {
+
+constexpr int TW = 64;  // tile width: 32 lanes x 2 outputs
+
+struct Args {
+    const uint8_t *joint;
+    const uint8_t *src;
+    uint8_t *dst;
+    const float *tab;  // device: (r+1) x nchunk float4, then (r+1) ints (even half widths)
+    int n, h, w, dc;
+    int r, rpad, pitch, nchunk;
+    float ksqrt;  // sqrt(0.5 / sigma_color^2 * log2 e) * alpha_scale
+};
+
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long ffma2r(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float ex2_neg(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(-x));
+    return y;
+}
+
+template <int WY, bool SEP>
+__global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
+{
+    extern __shared__ __align__(16) float smem_f[];
+    const int rows = WY + 2 * a.r;
+    const int tile = (rows * a.pitch + 3) & ~3;  // keeps the float4 table 16-byte aligned
+    float *tj = smem_f;
+    float *ts = SEP ? tj + tile : tj;
+    float4 *tab = reinterpret_cast<float4 *>(ts + tile);
+    const int *roww2 = reinterpret_cast<const int *>(tab + (a.r + 1) * a.nchunk);
+
+    const int img = blockIdx.z;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * WY;
+    const size_t npx = (size_t)a.h * a.w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const int cols = TW + 2 * a.rpad + 2;
+        const uint8_t *J = a.joint + img * npx;
+        const uint8_t *S = a.src + img * npx;
+        for (int yy = warp; yy < rows; yy += WY) {
+            const int gy = reflect101(ty0 - a.r + yy, a.h);
+            const uint8_t *jrow = J + (size_t)gy * a.w;
+            const uint8_t *srow = S + (size_t)gy * a.w;
+            for (int cc = lane; cc < cols; cc += 32) {
+                const int gx = reflect101(tx0 - a.rpad + cc, a.w);
+                tj[yy * a.pitch + cc] = (float)jrow[gx];
+                if (SEP) ts[yy * a.pitch + cc] = (float)srow[gx];
+            }
+        }
+        const int n4 = (a.r + 1) * a.nchunk * 4 + (a.r + 1);
+        float *t = reinterpret_cast<float *>(tab);
+        for (int i = threadIdx.x; i < n4; i += 32 * WY) t[i] = a.tab[i];
+    }
+    __syncthreads();
+
+    const int x0 = lane * 2;
+    const int ty = warp;
+    const float *jc_p = tj + (ty + a.r) * a.pitch + a.rpad + x0;
+    const unsigned long long jc2 = pack2(jc_p[0], jc_p[1]);
+    const unsigned long long neg1 = pack2(-1.0f, -1.0f);
+    const unsigned long long ks2 = pack2(a.ksqrt, a.ksqrt);
+    unsigned long long sum2 = 0ull, wsum2 = 0ull;
+    const int r = a.r;
+    for (int dyi = 0; dyi <= 2 * r; ++dyi) {
+        const int ady = dyi < r ? r - dyi : dyi - r;
+        const int w2 = roww2[ady];
+        // chunk t covers neighbours qb = 2t - rpad and qb + 1
+        const int t0 = (a.rpad - w2) >> 1, t1 = (a.rpad + w2) >> 1;
+        const float2 *jrow = reinterpret_cast<const float2 *>(tj + (ty + dyi) * a.pitch + x0);
+        const float2 *srow = reinterpret_cast<const float2 *>(ts + (ty + dyi) * a.pitch + x0);
+        const float4 *trow = tab + ady * a.nchunk;
+#pragma unroll 2
+        for (int t = t0; t <= t1; ++t) {
+            const float2 jn = jrow[t];
+            const float2 sn = SEP ? srow[t] : jn;
+            const float4 e = trow[t];
+            {   // neighbour qb: taps (p0: dx = qb, p1: dx = qb - 1)
+                const unsigned long long d2 = ffma2r(pack2(jn.x, jn.x), neg1, jc2);
+                const unsigned long long u2 = fmul2(d2, ks2);
+                const unsigned long long a2 = ffma2r(u2, u2, pack2(e.x, e.y));
+                float a0, a1;
+                unpack2(a2, a0, a1);
+                const unsigned long long w = pack2(ex2_neg(a0), ex2_neg(a1));
+                sum2 = ffma2r(pack2(sn.x, sn.x), w, sum2);
+                wsum2 = fadd2(wsum2, w);
+            }
+            {   // neighbour qb + 1: taps (p0: dx = qb + 1, p1: dx = qb)
+                const unsigned long long d2 = ffma2r(pack2(jn.y, jn.y), neg1, jc2);
+                const unsigned long long u2 = fmul2(d2, ks2);
+                const unsigned long long a2 = ffma2r(u2, u2, pack2(e.z, e.w));
+                float a0, a1;
+                unpack2(a2, a0, a1);
+                const unsigned long long w = pack2(ex2_neg(a0), ex2_neg(a1));
+                sum2 = ffma2r(pack2(sn.y, sn.y), w, sum2);
+                wsum2 = fadd2(wsum2, w);
+            }
+        }
+    }
+
+    const int gy = ty0 + ty;
+    if (gy >= a.h) return;
+    float s0, s1, w0, w1;
+    unpack2(sum2, s0, s1);
+    unpack2(wsum2, w0, w1);
+    uint8_t *drow = a.dst + (img * npx + (size_t)gy * a.w) * a.dc;
+    const float sv[2] = {s0, s1}, wv[2] = {w0, w1};
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int gx = tx0 + x0 + p;
+        if (gx >= a.w) break;
+        const uint8_t v = sat_u8(__fdiv_rn(sv[p], wv[p]));
+        uint8_t *o = drow + (size_t)gx * a.dc;
+        o[0] = v;
+        if (a.dc == 3) {
+            o[1] = v;
+            o[2] = v;
+        }
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+struct Geometry {
+    int r, rpad, pitch, nchunk;
+};
+
+static Geometry geometry(int r)
+{
+    Geometry g;
+    g.r = r;
+    g.rpad = (r + 1) & ~1;               // even
+    g.pitch = TW + 2 * g.rpad + 2;       // even: LDS.64 of a lane's two neighbours is always aligned
+    g.nchunk = g.rpad + 2;
+    return g;
+}
+
+struct TableEntry {
+    int device;
+    double sigma_space;
+    int r;
+    float *d_tab;
+};
+static std::mutex g_mu;
+static std::vector<TableEntry> g_tabs;
+
+// tab[ady][t] = (E(qb), E(qb-1), E(qb+1), E(qb)) with qb = 2t - rpad and
+// E(dx) = (dx^2 + ady^2) * 0.5 / sigma_space^2 * log2(e) inside the disc, +inf outside;
+// followed by the even-rounded half width of every row.
+static int get_table(double sigma_space, const Geometry &g, const float **out)
+{
+    int dev = 0;
+    RF_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (const TableEntry &e : g_tabs)
+        if (e.device == dev && e.sigma_space == sigma_space && e.r == g.r) {
+            *out = e.d_tab;
+            return RF_OK;
+        }
+    const int n = (g.r + 1) * g.nchunk * 4 + (g.r + 1);
+    std::vector<float> h(n);
+    const double gs = 0.5 / (sigma_space * sigma_space) * 1.4426950408889634074;
+    auto E = [&](int dx, int ady) -> float {
+        const int d2 = dx * dx + ady * ady;
+        return d2 <= g.r * g.r ? (float)(d2 * gs) : INFINITY;
+    };
+    for (int ady = 0; ady <= g.r; ++ady) {
+        for (int t = 0; t < g.nchunk; ++t) {
+            const int qb = 2 * t - g.rpad;
+            float *e = &h[(ady * g.nchunk + t) * 4];
+            e[0] = E(qb, ady);
+            e[1] = E(qb - 1, ady);
+            e[2] = E(qb + 1, ady);
+            e[3] = E(qb, ady);
+        }
+        const int hw = (int)std::floor(std::sqrt((double)(g.r * g.r - ady * ady)));
+        reinterpret_cast<int *>(h.data())[(g.r + 1) * g.nchunk * 4 + ady] = (hw + 1) & ~1;
+    }
+    float *d = nullptr;
+    RF_CUDA_TRY(cudaMalloc(&d, n * sizeof(float)));
+    RF_CUDA_TRY(cudaMemcpy(d, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    if (g_tabs.size() >= 64) {
+        for (size_t i = 0; i < g_tabs.size(); ++i)
+            if (g_tabs[i].device == dev) {
+                cudaFree(g_tabs[i].d_tab);
+                g_tabs.erase(g_tabs.begin() + i);
+                break;
+            }
+    }
+    g_tabs.push_back({dev, sigma_space, g.r, d});
+    *out = d;
+    return RF_OK;
+}
+
+static size_t smem_bytes(int wy, const Geometry &g, bool sep)
+{
+    const size_t tile = (((size_t)(wy + 2 * g.r) * g.pitch + 3) & ~(size_t)3) * 4;
+    return tile * (sep ? 2 : 1) + ((size_t)(g.r + 1) * g.nchunk * 4 + (g.r + 1)) * 4;
+}
+
+template <int WY, bool SEP>
+static int launch(const Args &a, size_t smem, cudaStream_t st)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    RF_CUDA_TRY(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        RF_CUDA_TRY(cudaFuncSetAttribute(bf_gray2_kernel<WY, SEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured[dev & 63] = true;
+    }
+    dim3 grid((a.w + TW - 1) / TW, (a.h + WY - 1) / WY, a.n);
+    bf_gray2_kernel<WY, SEP><<<grid, 32 * WY, smem, st>>>(a);
+    RF_LAUNCH_CHECK("bf_gray2_kernel");
+    return RF_OK;
+}
+
+int run(const uint8_t *joint, const uint8_t *src, uint8_t *dst, int n, int h, int w, int r, double sigma_color,
+        double sigma_space, double alpha_scale, cudaStream_t st)
+{
+    const Geometry g = geometry(r);
+    Args a;
+    a.joint = joint;
+    a.src = src;
+    a.dst = dst;
+    a.n = n;
+    a.h = h;
+    a.w = w;
+    a.dc = 1;
+    a.r = g.r;
+    a.rpad = g.rpad;
+    a.pitch = g.pitch;
+    a.nchunk = g.nchunk;
+    a.ksqrt = (float)(std::sqrt(0.5 / (sigma_color * sigma_color) * 1.4426950408889634074) * alpha_scale);
+    int rc = get_table(sigma_space, g, &a.tab);
+    if (rc != RF_OK) return rc;
+    const bool sep = joint != src;
+    // rows per CTA: big tiles amortise the window fill, small ones balance small grids over the SMs
+    const long tiles16 = (long)((w + TW - 1) / TW) * ((h + 15) / 16) * n;
+    int wy = 16;
+    if (tiles16 < 4L * sm_count()) wy = 8;
+    if (tiles16 < 1L * sm_count()) wy = 4;
+    while (wy > 4 && smem_bytes(wy, g, sep) > 100 * 1024) wy >>= 1;
+    const size_t smem = smem_bytes(wy, g, sep);
+    if (smem > 227 * 1024) return fail(RF_EUNSUPPORTED, "bf_gray2: radius %d needs %zu bytes of shared memory", r, smem);
+#define RF_BF2(WY)                                                                            \
+    case WY:                                                                                  \
+        return sep ? launch<WY, true>(a, smem, st) : launch<WY, false>(a, smem, st)
+    switch (wy) {
+        RF_BF2(4);
+        RF_BF2(8);
+        RF_BF2(16);
+    }
+#undef RF_BF2
+    return fail(RF_EINVAL, "bf_gray2: internal dispatch error");
+}
+
+}  // namespace bf2
+}  // namespace rf

@@ -21,6 +21,8 @@
 //   * no FP64: the box mean is float(S) * float(1/k^2) (<= 1 ulp from OpenCV's float(double(S)/k^2);
 //     measured effect ~2.5e-5 of the output bytes move by 1 LSB); pass B accumulates the
 //     coefficient planes in FP32 the same way.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rf {
@@ -424,7 +426,14 @@ static int halo(int r) { return (r + 1 + 3) & ~3; }
 // + 16: the chunk (<= 16 columns) that holds the right-most needed column must lie inside the row
 static int pitch(int w, int r) { return (w + 2 * halo(r) + 16 + 3) & ~3; }
 
-static Plan make_plan(int n, int h, int w, int r, int sms, int warps_per_cta)
+// tuning overrides (development only): RF_GF2_SEGS_A / RF_GF2_SEGS_B force the number of row segments
+static int env_int(const char *name)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
+static Plan make_plan(int h, int w, int r)
 {
     Plan best{};
     long best_cost = -1;
@@ -440,17 +449,6 @@ static Plan make_plan(int n, int h, int w, int r, int sms, int warps_per_cta)
             best_cost = cost;
             best = Plan{C, strips, twe, rh, pitch(w, r), 1, h};
         }
-    }
-    // split rows when the grid cannot fill the SMs; a warm-up row costs only its accumulate (about a
-    // quarter of a full row), so fairly short segments are fine
-    const long ctas = (long)best.strips * n;
-    const long want = (long)sms * 16 / warps_per_cta;  // ~16 resident warps per SM
-    if (ctas < want) {
-        int segs = (int)((want + ctas - 1) / ctas);
-        const int max_segs = h / 64 > 1 ? h / 64 : 1;
-        if (segs > max_segs) segs = max_segs;
-        best.segs = segs;
-        best.seg_rows = (h + segs - 1) / segs;
     }
     return best;
 }
@@ -472,9 +470,33 @@ static int launch(Args a, const Plan &p, cudaStream_t st)
     dim3 pgrid((a.wp + 255) / 256, a.h, a.n);
     pack_kernel<SC><<<pgrid, 256, 0, st>>>(a);
     RF_LAUNCH_CHECK("gf2::pack_kernel");
-    dim3 grid(p.strips, (a.h + p.seg_rows - 1) / p.seg_rows, a.n);
+    // Row segments: the vertical sums make a column strictly sequential, so small batches are split into
+    // row segments (each pays 2r warm-up rows) until the grid fills ONE wave of resident CTAs -- measured:
+    // more than one wave loses to tail effects, fewer leaves SMs idle (profiles/r01_gf2_segments.txt).
+    static int occ_a = 0, occ_b = 0;
+    if (occ_a == 0) {
+        RF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, pass_a_kernel<SC, C>, 32 * n_groups<SC>(), smem_a));
+        RF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, pass_b_kernel<SC, C>, 32 * 4 * SC, smem_b));
+        if (occ_a < 1) occ_a = 1;
+        if (occ_b < 1) occ_b = 1;
+    }
+    static const int force_a = env_int("RF_GF2_SEGS_A"), force_b = env_int("RF_GF2_SEGS_B");
+    const long ctas = (long)p.strips * a.n;
+    const int max_segs = a.h / 64 > 1 ? a.h / 64 : 1;
+    auto pick = [&](int occ, int forced) {
+        if (forced > 0) return forced;
+        long s = (long)sm_count() * occ / ctas;
+        if (s < 1) s = 1;
+        if (s > max_segs) s = max_segs;
+        return (int)s;
+    };
+    const int sa = pick(occ_a, force_a), sb = pick(occ_b, force_b);
+    a.seg_rows = (a.h + sa - 1) / sa;
+    dim3 grid(p.strips, (a.h + a.seg_rows - 1) / a.seg_rows, a.n);
     pass_a_kernel<SC, C><<<grid, 32 * n_groups<SC>(), smem_a, st>>>(a);
     RF_LAUNCH_CHECK("gf2::pass_a_kernel");
+    a.seg_rows = (a.h + sb - 1) / sb;
+    grid = dim3(p.strips, (a.h + a.seg_rows - 1) / a.seg_rows, a.n);
     pass_b_kernel<SC, C><<<grid, 32 * 4 * SC, smem_b, st>>>(a);
     RF_LAUNCH_CHECK("gf2::pass_b_kernel");
     return RF_OK;
@@ -503,7 +525,7 @@ int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws
     a.eps = (float)eps;
     const int k = 2 * r + 1;
     a.inv_area = (float)(1.0 / ((double)k * k));
-    const Plan p = make_plan(n, h, w, r, sm_count(), sc == 1 ? 4 : 6);
+    const Plan p = make_plan(h, w, r);
     a.rh = p.rh;
     a.wp = p.wp;
     a.twe = p.twe;
