@@ -12,7 +12,7 @@ path).  Inputs rotate through a pool larger than L2 so no step re-reads cached i
 `value`   : device-resident uint8 in -> uint8 out, CUDA-event time over exactly K steps, max over ranks.
 `e2e`     : the same steps through Pipeline.run_host: pinned HOST buffers in, HOST buffers out, H2D
             and D2H copies inside the timed region.
-`roofline`: the dominant kernel (bf_gray_kernel), timed per launch with CUDA events in a second pass
+`roofline`: the dominant kernel (bf_gray2_kernel), timed per launch with CUDA events in a second pass
             over the same steps.
 `cpu_baseline`: the reference-equivalent CPU path (cv2.dnn on the real prototxt/caffemodel +
             cv2.bilateralFilter, bit-identical to the restated jointBilateralFilter_8u) on a
@@ -234,7 +234,7 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     # ---- end to end through host buffers ----------------------------------------------------------
     def e2e_step(i):
         p = i % n_pool
-        pipe.run_host("cnn_bf", host_pool[p], host_out[p], chunk=args.chunk, n_streams=3,
+        pipe.run_host("cnn_bf", host_pool[p], host_out[p], chunk=args.chunk, n_streams=4,
                       sigma_color=SIGMA_COLOR, sigma_spatial=SIGMA_SPATIAL)
 
     for i in range(min(args.warmup, 3)):
@@ -315,7 +315,7 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     alu_peak = sms * 128 * f_max
     achieved_taps = taps_per_launch / (bf_ms * 1e-3)
     roofline = {
-        "kernel": "bf_gray_kernel", "bound": "sfu", "achieved": achieved_taps / 1e9, "peak": sfu_peak / 1e9,
+        "kernel": "bf_gray2_kernel", "bound": "sfu", "achieved": achieved_taps / 1e9, "peak": sfu_peak / 1e9,
         "unit": "Gtap/s (1 MUFU.EX2 per tap; peak = SMs*16*sm_max_mhz)", "frac": achieved_taps / sfu_peak,
         "frac_at_observed_clock": (achieved_taps / (sms * 16 * f_obs)) if f_obs else None,
         "fp32_lane_ops": {"per_tap": 4, "achieved_Gop_s": achieved_taps * 4 / 1e9, "peak_Gop_s": alu_peak / 1e9,
@@ -365,7 +365,7 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
             "workload": "configs[2]: %d x 512x384, CNN -> GF(CNN, flat guide) c3.0 s45.0 (r=45), 3 iterations, "
                         "uint8 re-quantisation between iterations" % gf["batch"],
             "value": world * gpx / (gf["ms_per_step"] * 1e-3) / 1e6, "unit": "MP/s", "ms_per_step": gf["ms_per_step"],
-            "roofline": {"kernel": "gf_pass_a<1> + gf_pass_b<1> (one iteration)", "bound": "hbm", "achieved": ach,
+            "roofline": {"kernel": "gf2 pack + pass_a<1> + pass_b<1> (one iteration)", "bound": "hbm", "achieved": ach,
                          "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "bytes_per_pixel": bpp,
                          "launch_ms": gf["gf_iteration_ms"], "traffic": None, "peak_source": peak_src}}
     print(json.dumps(line))
@@ -380,7 +380,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per step per GPU")
-    ap.add_argument("--chunk", type=int, default=16, help="images per H2D/compute/D2H chunk in the e2e path")
+    ap.add_argument("--chunk", type=int, default=8, help="images per H2D/compute/D2H chunk in the e2e path")
     ap.add_argument("--cpu-images", type=int, default=6, help="sample size of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gf", action="store_true", help="skip the secondary configs[2] (CNN->GF x3) measurement")

@@ -51,7 +51,8 @@ class Net(object):
                 pass
             self._handle = None
 
-    def forward_device(self, images: torch.Tensor, want_f32: bool = True, want_u8: bool = False):
+    def forward_device(self, images: torch.Tensor, want_f32: bool = True, want_u8: bool = False,
+                       out_f32: torch.Tensor = None, out_u8: torch.Tensor = None):
         """``uint8[N,H,W,3]`` BGR CUDA tensor -> (``float32[N,H,W]`` linear reflectance intensity
         or None, ``uint8[N,H,W]`` = trunc(r * 255) or None); asynchronous on the current stream."""
         dev.check_u8_cuda(images, "images")
@@ -60,8 +61,15 @@ class Net(object):
         if images.device != self.device:
             raise ValueError("images live on %s, the network on %s" % (images.device, self.device))
         n, h, w, _ = images.shape
-        f32 = torch.empty((n, h, w), dtype=torch.float32, device=self.device) if want_f32 else None
-        u8 = torch.empty((n, h, w), dtype=torch.uint8, device=self.device) if want_u8 else None
+        f32 = u8 = None
+        if want_f32:
+            f32 = out_f32 if out_f32 is not None else torch.empty((n, h, w), dtype=torch.float32, device=self.device)
+        if want_u8:
+            u8 = out_u8 if out_u8 is not None else torch.empty((n, h, w), dtype=torch.uint8, device=self.device)
+        for t, dt in ((f32, torch.float32), (u8, torch.uint8)):
+            if t is not None and (t.dtype != dt or tuple(t.shape) != (n, h, w) or not t.is_contiguous()
+                                  or t.device != self.device):
+                raise ValueError("output buffer must be a contiguous %s [N,H,W] tensor on %s" % (dt, self.device))
         with torch.cuda.device(self.device):
             dev.bind_device(self.device)
             _native.check(_native.lib().rf_cnn_forward_u8(

@@ -38,17 +38,19 @@ class Pipeline(object):
     def __init__(self, net: Optional[cnn.Net] = None, device=None):
         self.net = net if net is not None else cnn.default_net(device)
         self.device = self.net.device
+        self._host_ctx = {}
 
     # ---- device-resident stages ------------------------------------------------------------
-    def reflectance_u8(self, images: torch.Tensor) -> torch.Tensor:
+    def reflectance_u8(self, images: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``uint8[N,H,W,3]`` BGR -> ``uint8[N,H,W]``: the bytes of ``<base>-r.png``."""
-        return self.net.forward_device(images, want_f32=False, want_u8=True)[1]
+        return self.net.forward_device(images, want_f32=False, want_u8=True, out_u8=out)[1]
 
     def cnn_bf(self, images: torch.Tensor, sigma_color: float = 20.0, sigma_spatial: float = 22.0,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
         """BF(CNN, CNN): the CNN reflectance filtered with itself as guidance.  Returns the gray
-        plane ``uint8[N,H,W]`` (the reference's PNG has this value in all three channels)."""
-        r = self.reflectance_u8(images)
+        plane ``uint8[N,H,W]`` (the reference's PNG has this value in all three channels).
+        ``scratch``: optional ``uint8[N,H,W]`` buffer for the intermediate reflectance."""
+        r = self.reflectance_u8(images, out=scratch)
         return filters.joint_bilateral_device(r, r, sigma_color, sigma_spatial, d=-1,
                                               gray_replicated=True, out=out)
 
@@ -78,21 +80,41 @@ class Pipeline(object):
             raise ValueError("kind must be 'cnn_bf' or 'cnn_gf'")
         if kind == "cnn_gf" and guides is None:
             raise ValueError("cnn_gf needs guides")
-        n = images.shape[0]
+        n, h, w = images.shape[0], images.shape[1], images.shape[2]
         dev.bind_device(self.device)
-        streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+        # streams and per-stream device buffers are created once per (shape, chunk) and reused: fresh
+        # streams / allocations on every call cost tens of milliseconds of allocator traffic
+        key = (kind, chunk, h, w, max(1, n_streams))
+        ctx = self._host_ctx.get(key)
+        if ctx is None:
+            if len(self._host_ctx) > 8:
+                self._host_ctx.clear()
+            ctx = {"streams": [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))], "bufs": []}
+            for _ in ctx["streams"]:
+                b = {"img": torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=self.device),
+                     "r8": torch.empty((chunk, h, w), dtype=torch.uint8, device=self.device),
+                     "out": torch.empty((chunk, h, w), dtype=torch.uint8, device=self.device)}
+                if kind == "cnn_gf":
+                    b["guide"] = torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=self.device)
+                ctx["bufs"].append(b)
+            self._host_ctx[key] = ctx
+        streams = ctx["streams"]
         cur = torch.cuda.current_stream()
         for s in streams:
             s.wait_stream(cur)
         for ci, lo in enumerate(range(0, n, chunk)):
             hi = min(n, lo + chunk)
+            m = hi - lo
             s = streams[ci % len(streams)]
+            b = ctx["bufs"][ci % len(streams)]
             with torch.cuda.stream(s):
-                d_img = images[lo:hi].to(self.device, non_blocking=True)
+                d_img = b["img"][:m]
+                d_img.copy_(images[lo:hi], non_blocking=True)
                 if kind == "cnn_bf":
-                    res = self.cnn_bf(d_img, **params)
+                    res = self.cnn_bf(d_img, out=b["out"][:m], scratch=b["r8"][:m], **params)
                 else:
-                    d_gd = guides[lo:hi].to(self.device, non_blocking=True)
+                    d_gd = b["guide"][:m]
+                    d_gd.copy_(guides[lo:hi], non_blocking=True)
                     res = self.cnn_gf(d_img, d_gd, **params)
                 out[lo:hi].copy_(res, non_blocking=True)
         for s in streams:
