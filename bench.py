@@ -41,6 +41,16 @@ METRIC = "megapixels/sec end-to-end CNN->BF(CNN,CNN) c20 s22 (device-resident ui
 L2_BYTES = 126 * 1024 * 1024
 
 
+def make_config(batch, world, taps=3409, extra=None):
+    cfg = {"workload": "configs[1]: 512x384 CNN -> trunc u8 -> BF(CNN,CNN) c20 s22 (r=33, %d taps/px)" % taps,
+           "images_per_step_per_gpu": batch, "height": H, "width": W, "sigma_color": SIGMA_COLOR,
+           "sigma_spatial": SIGMA_SPATIAL,
+           "parallelism": "dp%d, contiguous image shards, no collective" % world}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -149,8 +159,9 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": mps, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 weights/sums, u8 pixels", "data": "synthetic",
-        "config": {"workload": "configs[1]: 512x384 CNN -> BF(CNN,CNN) c20 s22", "images_per_step": n_img,
-                   "height": H, "width": W, "sigma_color": SIGMA_COLOR, "sigma_spatial": SIGMA_SPATIAL},
+        "config": make_config(args.batch, max(1, args.gpus),
+                              extra={"reference_sample": "each step times %d image(s) of this workload on the host "
+                                                         "CPU (bounded sample)" % n_img}),
         "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
                          "sample": "%d step(s) x %d image(s) of 512x384: cv2.dnn forward on the reference "
                                    "prototxt+caffemodel, trunc, cv2.bilateralFilter c20 s22; cv2 threads=%d"
@@ -340,10 +351,8 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 weights/sums, u8 pixels", "data": "synthetic",
-        "config": {"workload": "configs[1]: 512x384 CNN -> trunc u8 -> BF(CNN,CNN) c20 s22 (r=33, %d taps/px)" % taps,
-                   "images_per_step_per_gpu": B, "height": H, "width": W, "sigma_color": SIGMA_COLOR,
-                   "sigma_spatial": SIGMA_SPATIAL, "cache": "inputs rotate through a %d-batch pool (%.0f MB > L2)"
-                   % (n_pool, n_pool * batch_bytes / 1e6), "parallelism": "dp%d, contiguous image shards, no collective" % world},
+        "config": make_config(B, world, taps, extra={"cache": "inputs rotate through a %d-batch pool (%.0f MB > L2)"
+                                                                 % (n_pool, n_pool * batch_bytes / 1e6)}),
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": world * batch_bytes,
                 "d2h_bytes_per_step": world * px_step, "ms_per_step": e2e_ms / args.steps,
                 "api": "Pipeline.run_host(pinned host uint8[N,H,W,3] -> pinned host uint8[N,H,W])",
