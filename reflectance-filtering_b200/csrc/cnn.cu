@@ -169,6 +169,15 @@ static int launch(const rf_cnn *net, const uint8_t *bgr, size_t n_px, float *out
 }  // namespace cnn
 }  // namespace rf
 
+namespace rf {
+namespace cnntc {  // cnn_tc.cu: tcgen05 / TMEM kernel for hidden width 32
+bool supported(int width, int n_hidden);
+bool disabled_by_env();
+int launch(const float *d_params, int n_hidden, const float *d_lut, const uint8_t *bgr, size_t n_px, float *out_f32,
+           uint8_t *out_u8, cudaStream_t st);
+}  // namespace cnntc
+}  // namespace rf
+
 using namespace rf;
 
 extern "C" int rf_cnn_create(const float *params, const int *dims, int n_hidden, const float *srgb_lut256,
@@ -238,6 +247,8 @@ extern "C" int rf_cnn_forward_u8(const rf_cnn *net, const uint8_t *bgr, int n, i
         return fail(RF_EINVAL, "rf_cnn_forward_u8: model lives on device %d, current device is %d", net->device, dev);
     const size_t n_px = (size_t)n * h * w;
     cudaStream_t st = (cudaStream_t)stream;
+    if (cnntc::supported(net->width, net->n_hidden) && !cnntc::disabled_by_env())
+        return cnntc::launch(net->d_params, net->n_hidden, net->d_lut, bgr, n_px, out_f32, out_u8, st);
     switch (net->width) {
         case 8: return cnn::launch<8>(net, bgr, n_px, out_f32, out_u8, st);
         case 16: return cnn::launch<16>(net, bgr, n_px, out_f32, out_u8, st);
