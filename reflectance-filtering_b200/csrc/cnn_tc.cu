@@ -13,7 +13,9 @@
 //   * activations never leave the SM: epilogue = tcgen05.ld (thread t of warp w owns TMEM lane 32w+t =
 //     pixel t of the tile, all 32 outputs) -> +bias, ReLU, fuse FMA, split -> st.shared in the canonical
 //     K-major (no-swizzle) UMMA layout -> fence.proxy.async -> next layer's MMAs;
-//   * persistent CTAs (weights staged once per CTA), 3 CTAs per SM overlap each other's MMA latency.
+//   * persistent CTAs of two warpgroups, each warpgroup runs its own tile pipeline (own A planes, TMEM
+//     columns, mbarrier, named barrier) over weights staged once per CTA; 2 CTAs per SM = four pipelines
+//     overlapping each other's MMA / barrier latency.
 // SASS: UTCHMMA / LDTM / UTCBAR (tcgen05.mma / .ld / .commit).  The exact-FP32 kernel in cnn.cu remains
 // for other widths and as the in-library cross-check (RF_CNN_FP32=1).
 #include <cstdlib>
@@ -25,7 +27,8 @@ namespace cnntc {
 
 constexpr int TILE_M = 128;
 constexpr int CW = 32;  // hidden width
-constexpr int THREADS = 128;
+constexpr int WGS = 2;            // warpgroups per CTA, each runs its own tile pipeline
+constexpr int THREADS = 128 * WGS;
 constexpr int A_BYTES = TILE_M * CW * 4;  // 16 KB per operand plane
 constexpr int B_BYTES = CW * CW * 4;      // 4 KB per weight plane
 
@@ -85,15 +88,15 @@ struct Smem {
 __host__ __device__ inline Smem smem_map(int n_hidden)
 {
     Smem s;
-    s.a_hi = 0;
+    s.a_hi = 0;                                        // warpgroup g: a_hi + g * 2 * A_BYTES
     s.a_lo = A_BYTES;
-    s.b = 2 * A_BYTES;                                 // per MMA layer: hi plane, lo plane
+    s.b = WGS * 2 * A_BYTES;                           // per MMA layer: hi plane, lo plane (shared by the warpgroups)
     s.w0 = s.b + (n_hidden - 1) * 2 * B_BYTES;         // 32 x 3 floats (padded to 128)
     s.bias = s.w0 + 128 * 4;                           // n_hidden x 32
     s.fw = s.bias + n_hidden * CW * 4;                 // n_hidden x 32, then fuse bias
     s.lut = s.fw + (n_hidden * CW + 4) * 4;            // 256
-    s.bar = s.lut + 256 * 4;                           // 8-byte mbarrier
-    s.slot = s.bar + 8;
+    s.bar = s.lut + 256 * 4;                           // one 8-byte mbarrier per warpgroup
+    s.slot = s.bar + 8 * WGS;
     s.total = s.slot + 8;
     return s;
 }
@@ -105,19 +108,25 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const Smem sm = smem_map(n_hidden);
-    float *A_hi = reinterpret_cast<float *>(smem + sm.a_hi);
-    float *A_lo = reinterpret_cast<float *>(smem + sm.a_lo);
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, wtid = tid & 127;
+    float *A_hi = reinterpret_cast<float *>(smem + sm.a_hi + wg * 2 * A_BYTES);
+    float *A_lo = reinterpret_cast<float *>(smem + sm.a_lo + wg * 2 * A_BYTES);
     float *Bw = reinterpret_cast<float *>(smem + sm.b);
     float *W0 = reinterpret_cast<float *>(smem + sm.w0);
     float *bias = reinterpret_cast<float *>(smem + sm.bias);
     float *fw = reinterpret_cast<float *>(smem + sm.fw);
     float *lut = reinterpret_cast<float *>(smem + sm.lut);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + sm.bar);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + sm.bar) + wg;
     uint32_t *slot = reinterpret_cast<uint32_t *>(smem + sm.slot);
-    const int tid = threadIdx.x, warp = tid >> 5;
 
     // ---- stage the model: parameter block is [W0 | b0 | W1 | b1 | ... | fuse_w | fuse_b] ----------------
-    for (int i = tid; i < 96; i += THREADS) W0[i] = params[i];
+    // conv0 as 32 x float4 (w_r, w_g, w_b, bias): one LDS.128 per output channel
+    for (int i = tid; i < CW; i += THREADS) {
+        W0[4 * i] = params[3 * i];
+        W0[4 * i + 1] = params[3 * i + 1];
+        W0[4 * i + 2] = params[3 * i + 2];
+        W0[4 * i + 3] = params[96 + i];
+    }
     for (int i = tid; i < 256; i += THREADS) lut[i] = lut_g[i];
     {
         const float *q = params + 96;
@@ -139,28 +148,29 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
         }
         for (int i = tid; i < n_hidden * CW + 1; i += THREADS) fw[i] = q[i];
     }
-    if (tid == 0) {
+    if (wtid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // weight planes -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *slot;
+    const uint32_t tmem_base = *slot;
+    const uint32_t tmem = tmem_base + wg * 32;  // 32 accumulator columns per warpgroup
     const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), b_s = smem_u32(Bw), bar_s = smem_u32(bar);
     const float fb = fw[n_hidden * CW];
 
     // this thread's row of the A planes: 8 chunks of 16 B, chunk kc at kc*2048 + (m/8)*128 + (m%8)*16
-    const int row_off = ((tid >> 3) * 128 + (tid & 7) * 16) >> 2;  // in floats
+    const int row_off = ((wtid >> 3) * 128 + (wtid & 7) * 16) >> 2;  // in floats
     uint32_t parity = 0;
     const size_t n_tiles = (n_px + TILE_M - 1) / TILE_M;
-    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const size_t p = tile * TILE_M + tid;
+    for (size_t tile = (size_t)blockIdx.x * WGS + wg; tile < n_tiles; tile += (size_t)gridDim.x * WGS) {
+        const size_t p = tile * TILE_M + wtid;
         const bool valid = p < n_px;
         const uint8_t *px = bgr + 3 * (valid ? p : n_px - 1);
         const float x0 = lut[px[2]], x1 = lut[px[1]], x2 = lut[px[0]];  // BGR -> RGB, sRGB -> linear
@@ -169,12 +179,18 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
         float z = 0.0f;
         // conv0 + ReLU on the CUDA cores (Caffe order: dot, + bias, ReLU)
 #pragma unroll
-        for (int o = 0; o < CW; ++o) {
-            float s = W0[o * 3] * x0;
-            s = fmaf(W0[o * 3 + 1], x1, s);
-            s = fmaf(W0[o * 3 + 2], x2, s);
-            h[o] = fmaxf(s + bias[o], 0.0f);
-            z = fmaf(fw[o], h[o], z);
+        for (int o = 0; o < CW; o += 4) {
+            const float4 f4 = *reinterpret_cast<const float4 *>(fw + o);
+            const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 w = *reinterpret_cast<const float4 *>(W0 + 4 * (o + u));
+                float s = w.x * x0;
+                s = fmaf(w.y, x1, s);
+                s = fmaf(w.z, x2, s);
+                h[o + u] = fmaxf(s + w.w, 0.0f);
+                z = fmaf(fv[u], h[o + u], z);
+            }
         }
         for (int l = 1; l < n_hidden; ++l) {
             // activations -> A planes (hi = the word itself, lo = what TF32 truncation drops)
@@ -187,8 +203,8 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
-            if (tid == 0) {
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");  // this warpgroup only
+            if (wtid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t bh = b_s + (l - 1) * 2 * B_BYTES, bl = bh + B_BYTES;
 #pragma unroll
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
             parity ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t acc[CW];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -222,11 +238,19 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const float *bl_ = bias + l * CW, *fl = fw + l * CW;
+            const float4 *bl_ = reinterpret_cast<const float4 *>(bias + l * CW);
+            const float4 *fl = reinterpret_cast<const float4 *>(fw + l * CW);
 #pragma unroll
-            for (int o = 0; o < CW; ++o) {
-                h[o] = fmaxf(__uint_as_float(acc[o]) + bl_[o], 0.0f);
-                z = fmaf(fl[o], h[o], z);
+            for (int o = 0; o < CW; o += 4) {
+                const float4 b4 = bl_[o >> 2], f4 = fl[o >> 2];
+                h[o] = fmaxf(__uint_as_float(acc[o]) + b4.x, 0.0f);
+                h[o + 1] = fmaxf(__uint_as_float(acc[o + 1]) + b4.y, 0.0f);
+                h[o + 2] = fmaxf(__uint_as_float(acc[o + 2]) + b4.z, 0.0f);
+                h[o + 3] = fmaxf(__uint_as_float(acc[o + 3]) + b4.w, 0.0f);
+                z = fmaf(f4.x, h[o], z);
+                z = fmaf(f4.y, h[o + 1], z);
+                z = fmaf(f4.z, h[o + 2], z);
+                z = fmaf(f4.w, h[o + 3], z);
             }
         }
         const float r = __fdiv_rn(1.0f, 1.0f + expf(-(z + fb)));
@@ -235,11 +259,11 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
             if (out_u8) out_u8[p] = (uint8_t)__float2int_rz(__fmul_rn(r, 255.0f));
         }
         // the next tile's A writes and MMAs are ordered behind this tile's TMEM reads by the
-        // before_thread_sync fence + __syncthreads at the top of its first MMA layer
+        // before_thread_sync fence + warpgroup barrier at the top of its first MMA layer
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
 }
 
 bool supported(int width, int n_hidden) { return width == CW && n_hidden >= 2 && n_hidden <= 8; }
@@ -265,14 +289,15 @@ int launch(const float *d_params, int n_hidden, const float *d_lut, const uint8_
     RF_CUDA_TRY(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
         RF_CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        int o = 0;
-        RF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, mlp_tc_kernel, THREADS, smem));
-        occ[dev & 63] = o < 1 ? 1 : o;
+        // resident CTAs per SM are bounded by shared memory (the occupancy API under-reports kernels that
+        // use TMEM); registers allow 6, TMEM (32 of 512 columns per CTA) allows 16
+        int o = (int)((227 * 1024) / (smem + 1024));
+        occ[dev & 63] = o < 1 ? 1 : (o > 6 ? 6 : o);
         configured[dev & 63] = true;
     }
     const size_t n_tiles = (n_px + TILE_M - 1) / TILE_M;
     size_t blocks = (size_t)sm_count() * occ[dev & 63];
-    if (blocks > n_tiles) blocks = n_tiles;
+    if (blocks > (n_tiles + WGS - 1) / WGS) blocks = (n_tiles + WGS - 1) / WGS;
     mlp_tc_kernel<<<(unsigned)blocks, THREADS, smem, st>>>(d_params, n_hidden, d_lut, bgr, n_px, out_f32, out_u8);
     RF_LAUNCH_CHECK("mlp_tc_kernel");
     return RF_OK;
