@@ -10,9 +10,12 @@
 //     TF32 misses the 1e-3 tolerance (7e-3), so operands are split x = hi + lo with
 //     hi = x truncated to TF32 (what the tensor core reads anyway) and lo = x - hi, and each layer issues
 //     A_hi*W_hi + A_hi*W_lo + A_lo*W_hi (12 MMAs); measured max error vs the FP32 oracle: ~3e-6;
-//   * activations never leave the SM: epilogue = tcgen05.ld (thread t of warp w owns TMEM lane 32w+t =
-//     pixel t of the tile, all 32 outputs) -> +bias, ReLU, fuse FMA, split -> st.shared in the canonical
-//     K-major (no-swizzle) UMMA layout -> fence.proxy.async -> next layer's MMAs;
+//   * activations never leave the SM and never touch shared memory: epilogue = tcgen05.ld (thread t of
+//     warp w owns TMEM lane 32w+t = pixel t of the tile, all 32 outputs) -> +bias, ReLU, fuse FMA, split
+//     -> tcgen05.st back into tensor memory as the A operand of the next layer's MMAs (A-from-TMEM form);
+//     only the 32x32 weight planes are read from shared memory (canonical K-major no-swizzle UMMA
+//     layout).  A first version staged A in shared memory and was bound by its bandwidth (67 % of
+//     the LSU wavefront peak, profiles/r01_cnn_tc_ncu_full.txt);
 //   * persistent CTAs of two warpgroups, each warpgroup runs its own tile pipeline (own A planes, TMEM
 //     columns, mbarrier, named barrier) over weights staged once per CTA; 2 CTAs per SM = four pipelines
 //     overlapping each other's MMA / barrier latency.
@@ -29,7 +32,6 @@ constexpr int TILE_M = 128;
 constexpr int CW = 32;  // hidden width
 constexpr int WGS = 2;            // warpgroups per CTA, each runs its own tile pipeline
 constexpr int THREADS = 128 * WGS;
-constexpr int A_BYTES = TILE_M * CW * 4;  // 16 KB per operand plane
 constexpr int B_BYTES = CW * CW * 4;      // 4 KB per weight plane
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,6 +63,33 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         : "memory");
 }
 
+// A operand from tensor memory (lanes = rows of the tile, one 32-bit column per TF32 element)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+// this thread's TMEM lane, 32 consecutive columns
+__device__ __forceinline__ void tmem_store32(uint32_t taddr, const float (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]),
+        "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]),
+        "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+        : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
@@ -88,9 +117,9 @@ struct Smem {
 __host__ __device__ inline Smem smem_map(int n_hidden)
 {
     Smem s;
-    s.a_hi = 0;                                        // warpgroup g: a_hi + g * 2 * A_BYTES
-    s.a_lo = A_BYTES;
-    s.b = WGS * 2 * A_BYTES;                           // per MMA layer: hi plane, lo plane (shared by the warpgroups)
+    s.a_hi = 0;                                        // (activations live in tensor memory)
+    s.a_lo = 0;
+    s.b = 0;                                           // per MMA layer: hi plane, lo plane (shared by the warpgroups)
     s.w0 = s.b + (n_hidden - 1) * 2 * B_BYTES;         // 32 x 3 floats (padded to 128)
     s.bias = s.w0 + 128 * 4;                           // n_hidden x 32
     s.fw = s.bias + n_hidden * CW * 4;                 // n_hidden x 32, then fuse bias
@@ -109,8 +138,6 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
     extern __shared__ __align__(1024) uint8_t smem[];
     const Smem sm = smem_map(n_hidden);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, wtid = tid & 127;
-    float *A_hi = reinterpret_cast<float *>(smem + sm.a_hi + wg * 2 * A_BYTES);
-    float *A_lo = reinterpret_cast<float *>(smem + sm.a_lo + wg * 2 * A_BYTES);
     float *Bw = reinterpret_cast<float *>(smem + sm.b);
     float *W0 = reinterpret_cast<float *>(smem + sm.w0);
     float *bias = reinterpret_cast<float *>(smem + sm.bias);
@@ -153,7 +180,7 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // weight planes -> visible to the tensor core
@@ -161,12 +188,12 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *slot;
-    const uint32_t tmem = tmem_base + wg * 32;  // 32 accumulator columns per warpgroup
-    const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), b_s = smem_u32(Bw), bar_s = smem_u32(bar);
+    // 128 columns per warpgroup: D = [0,32), A_hi = [32,64), A_lo = [64,96)
+    const uint32_t tmem = tmem_base + wg * 128;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // a warp may only touch its own 32 lanes
+    const uint32_t b_s = smem_u32(Bw), bar_s = smem_u32(bar);
     const float fb = fw[n_hidden * CW];
 
-    // this thread's row of the A planes: 8 chunks of 16 B, chunk kc at kc*2048 + (m/8)*128 + (m%8)*16
-    const int row_off = ((wtid >> 3) * 128 + (wtid & 7) * 16) >> 2;  // in floats
     uint32_t parity = 0;
     const size_t n_tiles = (n_px + TILE_M - 1) / TILE_M;
     for (size_t tile = (size_t)blockIdx.x * WGS + wg; tile < n_tiles; tile += (size_t)gridDim.x * WGS) {
@@ -193,15 +220,16 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
             }
         }
         for (int l = 1; l < n_hidden; ++l) {
-            // activations -> A planes (hi = the word itself, lo = what TF32 truncation drops)
+            // activations -> tensor memory: A_hi = the word itself (the tensor core truncates it to TF32),
+            // A_lo = what that truncation drops
+            {
+                float lo[CW];
 #pragma unroll
-            for (int kc = 0; kc < CW / 4; ++kc) {
-                const float4 vh = make_float4(h[4 * kc], h[4 * kc + 1], h[4 * kc + 2], h[4 * kc + 3]);
-                const float4 vl = make_float4(tf32_lo(vh.x), tf32_lo(vh.y), tf32_lo(vh.z), tf32_lo(vh.w));
-                *reinterpret_cast<float4 *>(A_hi + kc * 512 + row_off) = vh;
-                *reinterpret_cast<float4 *>(A_lo + kc * 512 + row_off) = vl;
+                for (int o = 0; o < CW; ++o) lo[o] = tf32_lo(h[o]);
+                tmem_store32(tmem + 32 + lane_sel, h);
+                tmem_store32(tmem + 64 + lane_sel, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");  // this warpgroup only
             if (wtid == 0) {
@@ -209,13 +237,12 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
                 const uint32_t bh = b_s + (l - 1) * 2 * B_BYTES, bl = bh + B_BYTES;
 #pragma unroll
                 for (int combo = 0; combo < 3; ++combo) {
-                    const uint32_t as = combo == 2 ? a_lo_s : a_hi_s;
+                    const uint32_t at = tmem + (combo == 2 ? 64 : 32);
                     const uint32_t bs = combo == 1 ? bl : bh;
 #pragma unroll
                     for (int j = 0; j < CW / 8; ++j) {
-                        const uint64_t ad = make_desc(as + j * 2 * 2048, 2048, 128);
                         const uint64_t bd = make_desc(bs + j * 2 * 512, 512, 128);
-                        mma_tf32(tmem, ad, bd, (combo | j) != 0);
+                        mma_tf32_ts(tmem, at + 8 * j, bd, (combo | j) != 0);
                     }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_s)
@@ -225,7 +252,7 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
             parity ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t acc[CW];
-            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            const uint32_t taddr = tmem + lane_sel;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -263,7 +290,7 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
 }
 
 bool supported(int width, int n_hidden) { return width == CW && n_hidden >= 2 && n_hidden <= 8; }
@@ -292,7 +319,7 @@ int launch(const float *d_params, int n_hidden, const float *d_lut, const uint8_
         // resident CTAs per SM are bounded by shared memory (the occupancy API under-reports kernels that
         // use TMEM); registers allow 6, TMEM (32 of 512 columns per CTA) allows 16
         int o = (int)((227 * 1024) / (smem + 1024));
-        occ[dev & 63] = o < 1 ? 1 : (o > 6 ? 6 : o);
+        occ[dev & 63] = o < 1 ? 1 : (o > 2 ? 2 : o);  // tensor memory: 256 of the SM's 512 columns per CTA
         configured[dev & 63] = true;
     }
     const size_t n_tiles = (n_px + TILE_M - 1) / TILE_M;
