@@ -275,6 +275,45 @@ def test_cli_end_to_end(tmp_path, net, mlp):
     assert mx <= 1 and frac < 2e-3
 
 
+def test_batch_front_end_matches_per_file_cli(tmp_path, net):
+    import cv2
+    from reflectance_filtering_b200 import batch
+    src_dir, out_a, out_b, gdir = (tmp_path / n for n in ("in", "batch", "single", "guide"))
+    for d in (src_dir, out_a, out_b, gdir):
+        d.mkdir()
+    shapes = [(40, 56), (40, 56), (33, 47), (40, 56), (33, 47)]
+    for i, (h, w) in enumerate(shapes):
+        cv2.imwrite(str(src_dir / ("im%d.png" % i)), synth.natural(h, w, 700 + i))
+        cv2.imwrite(str(gdir / ("im%d.png" % i)), synth.flat(h, w, 800 + i))
+    (src_dir / "broken.png").write_bytes(b"not a png")
+    files = batch.list_inputs(str(src_dir))
+    assert len(files) == 6
+    # chain CNN -> BF(CNN, CNN), two shards processed in reverse order
+    for rank in (1, 0):
+        res = batch.run_batch(files, str(out_a), mode="decompose+filter", filter_type="bilateral", sigma_color=20,
+                              sigma_spatial=22, chunk=2, rank=rank, world=2)
+        assert all("broken" in k for k in res["errors"])
+    for i in range(5):
+        f = str(src_dir / ("im%d.png" % i))
+        cnn.decompose_image(f, str(out_b), net=net)
+        filters.read_filter_write("bilateral", str(out_b / ("im%d-r.png" % i)), str(out_b / ("im%d-r.png" % i)),
+                                  20.0, 22.0, str(out_b))
+        for name in ("im%d-r.png" % i, "im%d-r_bilateral_c20.0s22.0.png" % i):
+            a = cv2.imread(str(out_a / name), cv2.IMREAD_UNCHANGED)
+            b = cv2.imread(str(out_b / name), cv2.IMREAD_UNCHANGED)
+            assert a is not None and a.shape == b.shape and np.array_equal(a, b), name
+    # filter-only mode with a guidance directory: 3 x GF on colour images
+    res = batch.run_batch(files[1:], str(out_a), mode="filter", filter_type="guided", sigma_color=3, sigma_spatial=7,
+                          guidance=str(gdir), iterations=3, chunk=4)
+    assert not res["errors"] and len(res["written"]) == 5
+    img = cv2.imread(str(src_dir / "im2.png"))
+    gd = cv2.imread(str(gdir / "im2.png"))
+    cur = img
+    for _ in range(3):
+        cur = filters.apply_filter("guided", cur, gd, 3.0, 7.0)
+    assert np.array_equal(cv2.imread(str(out_a / "im2_guided_c3.0s7.0.png")), cur)
+
+
 def test_native_library_is_the_one_loaded():
     from reflectance_filtering_b200 import _native
     before = _native.launch_count()
