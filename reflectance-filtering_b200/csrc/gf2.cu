@@ -383,7 +383,10 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
                 const float tt = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += tt;
             }
-            const float excl = incl - run;
+            // exclusive prefix by a shift, NOT incl - run: the chunk right of the last needed column may hold
+            // unwritten coefficients (inf/NaN garbage), and inf - inf would poison this lane's own prefix
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 0.0f;
             float *dstp = P + pl * NX + lane * C;
 #pragma unroll
             for (int c = 0; c < C; c += 4)

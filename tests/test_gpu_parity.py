@@ -184,6 +184,20 @@ def test_gf_matches_oracle(h, w, r, eps, sc):
     assert out.shape == ref.shape and mx <= 1 and frac < 2e-3, (mx, frac)
 
 
+@pytest.mark.parametrize("h,w,r,sc", [(33, 47, 7, 3), (33, 47, 7, 1), (40, 57, 12, 1), (64, 100, 20, 3)])
+def test_gf_ignores_workspace_contents(h, w, r, sc):
+    # the workspace is scratch: results must not depend on what it held (regression: inf - inf in a prefix)
+    gd = synth.flat(h, w, 802)
+    src = synth.natural(h, w, 702)
+    src = src if sc == 3 else src[:, :, 0].copy()
+    ref = oracle.guided(gd, src, r, 3.0)
+    for fill in (float("nan"), 3e38, -3e38):
+        ws = torch.full((8 << 20,), fill, dtype=torch.float32, device="cuda").view(torch.uint8)
+        out = filters.guided_device(dev_u8(gd[None]), dev_u8(src[None]), r, 3.0, workspace=ws).cpu().numpy()[0]
+        mx, frac = lsb(out, ref)
+        assert mx <= 1 and frac < 2e-3, (fill, mx, frac)
+
+
 def test_gf_full_size_three_iterations_and_properties(net):
     # BASELINE config 3 on one image: CNN reflectance, 'flat' guide, c3 s45, 3 iterations with uint8
     # re-quantisation between them
