@@ -194,7 +194,7 @@ def test_gf_ignores_workspace_contents(h, w, r, sc):
     for fill in (float("nan"), 3e38, -3e38):
         ws = torch.full((8 << 20,), fill, dtype=torch.float32, device="cuda").view(torch.uint8)
         out = filters.guided_device(dev_u8(gd[None]), dev_u8(src[None]), r, 3.0, workspace=ws).cpu().numpy()[0]
-        mx, frac = lsb(out, ref)
+        mx, frac = lsb_stats(out, ref)
         assert mx <= 1 and frac < 2e-3, (fill, mx, frac)
 
 
