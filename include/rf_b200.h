@@ -14,7 +14,7 @@
  *                                       sigmaSpace)        filter_reflectance.py:60-64
  *   rf_guided_u8                        cv2.ximgproc.guidedFilter(guide, src, radius, eps)
  *                                                          filter_reflectance.py:67-70
- *   rf_colorize_*                       image_utils.colorize / normalize / rgb_to_srgb / imwrite
+ *   rf_colorize_u8                      image_utils.colorize / normalize / rgb_to_srgb / imwrite
  *                                       quantisation       image_utils.py:42-49,60-92
  *
  * Conventions
@@ -105,6 +105,18 @@ int rf_replicate_gray_u8(const uint8_t *gray, uint8_t *bgr, size_t n_px, void *s
  * pixel has unequal channels; it is never set by this call */
 int rf_extract_gray_u8(const uint8_t *bgr, uint8_t *gray, size_t n_px, int *all_equal_flag,
                        void *stream);
+
+/* ---- colorized side outputs of the decomposition (decompose_with_trained_CNN.py:122-128) ----------------
+ * For every image: colorize (image_utils.py:76-81) on the raw 0..255 BGR image and the float32 reflectance
+ * intensity, then what imwrite(..., sRGB=True) does to each result (image_utils.py:60-92): divide by the
+ * 99.9th percentile ('lower' selection) and clip if max > 1, the reference's rgb_to_srgb, truncate to uint8.
+ * All arithmetic in float64 as numpy does.  k_reflectance / k_shading: 0-based rank of the percentile
+ * element among the 3*h*w reflectance / h*w shading values = floor((count - 1) * (99.9 / 100)) evaluated by
+ * the caller in float64 (numpy's own formula).  out_reflectance [n][h][w][3] (BGR order), out_shading [n][h][w]. */
+size_t rf_colorize_workspace_bytes(int n, int h, int w);
+int rf_colorize_u8(const uint8_t *bgr, const float *intensity, int n, int h, int w, double eps,
+                   unsigned long long k_reflectance, unsigned long long k_shading, uint8_t *out_reflectance,
+                   uint8_t *out_shading, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- aggregate statistics (the one value a multi-GPU run may all-reduce) --------------------
  * stats[0] += n_px ; [1] += sum(out) ; [2] += sum(out^2) ; [3] += sum|out - in| ; device doubles */

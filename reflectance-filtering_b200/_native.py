@@ -38,6 +38,8 @@ SIGNATURES = {
     "rf_replicate_gray_u8": (_i, [_vp, _vp, _sz, _vp]),
     "rf_extract_gray_u8": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "rf_accumulate_stats_u8": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "rf_colorize_workspace_bytes": (_sz, [_i, _i, _i]),
+    "rf_colorize_u8": (_i, [_vp, _vp, _i, _i, _i, _d, C.c_ulonglong, C.c_ulonglong, _vp, _vp, _vp, _sz, _vp]),
 }
 
 

@@ -116,6 +116,36 @@ def get_reflectance_caffe(net, image):
 get_reflectance = get_reflectance_caffe
 
 
+def percentile_rank(count: int, q: float = 99.9) -> int:
+    """0-based rank np.percentile(..., q, method='lower') selects among ``count`` values, with numpy's own
+    float64 arithmetic: floor((count - 1) * (q / 100))."""
+    return int(np.floor((count - 1) * np.true_divide(np.float64(q), 100)))
+
+
+def colorize_device(images: torch.Tensor, intensity: torch.Tensor, eps: float = 1e-3):
+    """Device version of ``iu.colorize`` followed by ``iu.imwrite(..., sRGB=True)``'s quantisation, for a
+    batch: ``uint8[N,H,W,3]`` BGR + ``float32[N,H,W]`` -> (``uint8[N,H,W,3]`` colorized reflectance,
+    ``uint8[N,H,W]`` shading) = the bytes of ``<base>-r_colorized.png`` / ``<base>-s_colorized.png``
+    (decompose_with_trained_CNN.py:122-128)."""
+    dev.check_u8_cuda(images, "images")
+    if images.dim() != 4 or images.shape[3] != 3:
+        raise ValueError("images must be [N,H,W,3]")
+    n, h, w, _ = images.shape
+    if intensity.dtype != torch.float32 or tuple(intensity.shape) != (n, h, w) or not intensity.is_cuda \
+            or not intensity.is_contiguous():
+        raise ValueError("intensity must be a contiguous CUDA float32 [N,H,W] tensor")
+    L = _native.lib()
+    out_r = torch.empty((n, h, w, 3), dtype=torch.uint8, device=images.device)
+    out_s = torch.empty((n, h, w), dtype=torch.uint8, device=images.device)
+    with torch.cuda.device(images.device):
+        dev.bind_device(images.device)
+        ws = torch.empty(int(L.rf_colorize_workspace_bytes(n, h, w)), dtype=torch.uint8, device=images.device)
+        _native.check(L.rf_colorize_u8(dev.ptr(images), dev.ptr(intensity), n, h, w, float(eps),
+                                       percentile_rank(3 * h * w), percentile_rank(h * w), dev.ptr(out_r),
+                                       dev.ptr(out_s), dev.ptr(ws), ws.numel(), dev.stream_ptr()))
+    return out_r, out_s
+
+
 def decompose_image(filename_in, path_out, net=None):
     """Run the intrinsic image decomposition (decompose...py:98-130): writes ``<base>-r.png``
     (linear gray), ``<base>-r_colorized.png`` and ``<base>-s_colorized.png`` (sRGB) into
@@ -124,9 +154,14 @@ def decompose_image(filename_in, path_out, net=None):
         net = default_net()
     image = iu.imread(filename_in)
     stem = os.path.splitext(os.path.basename(filename_in))[0]
-    reflectance_gray = get_reflectance_caffe(net, image)
-    iu.imwrite(os.path.join(path_out, stem + '-r.png'), reflectance_gray)
-    reflectance, shading = iu.colorize(reflectance_gray, image)
-    iu.imwrite(os.path.join(path_out, stem + '-r_colorized.png'), reflectance, sRGB=True)
-    iu.imwrite(os.path.join(path_out, stem + '-s_colorized.png'), shading, sRGB=True)
+    # one upload; the reflectance, its truncated uint8 form and both colorized outputs are produced on the
+    # device with the reference's quantisation points, then written with cv2 exactly as iu.imwrite would
+    dev.bind_device(net.device)
+    t = dev.to_device(image, "cnn_in")[None]
+    f32, u8 = net.forward_device(t, want_f32=True, want_u8=True)
+    refl_u8, shad_u8 = colorize_device(t, f32)
+    reflectance_gray = dev.to_host(f32, "cnn_out")[0]
+    iu.imwrite(os.path.join(path_out, stem + '-r.png'), dev.to_host(u8, "cnn_u8")[0])
+    iu.imwrite(os.path.join(path_out, stem + '-r_colorized.png'), dev.to_host(refl_u8, "col_r")[0])
+    iu.imwrite(os.path.join(path_out, stem + '-s_colorized.png'), dev.to_host(shad_u8, "col_s")[0])
     return reflectance_gray

@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
        -Xcompiler -Wall -Wno-deprecated-gpu-targets -ccbin /usr/bin/g++)
 OBJS=()
-for f in misc bf bf2 cnn cnn_tc gf gf2; do
+for f in misc bf bf2 cnn cnn_tc gf gf2 colorize; do
   "$NVCC" "${FLAGS[@]}" ${RF_PTXAS_V:+-Xptxas -v} -c "$f.cu" -o "$f.o" &
   OBJS+=("$f.o")
 done
