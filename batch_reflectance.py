@@ -32,6 +32,7 @@ def main(argv=None):
     ap.add_argument("--chunk", type=int, default=16)
     ap.add_argument("--io_threads", type=int, default=8)
     ap.add_argument("--skip_existing", action="store_true")
+    ap.add_argument("--colorized", action="store_true", help="also write <name>-r_colorized.png / <name>-s_colorized.png")
     args = ap.parse_args(argv)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -41,7 +42,7 @@ def main(argv=None):
     res = batch.run_batch(files, args.path_out, mode=args.mode, filter_type=args.filter_type,
                           sigma_color=args.sigma_color, sigma_spatial=args.sigma_spatial, guidance=args.guidance_dir,
                           iterations=args.iterations, device=local, io_threads=args.io_threads, chunk=args.chunk,
-                          rank=rank, world=world, skip_existing=args.skip_existing)
+                          rank=rank, world=world, skip_existing=args.skip_existing, colorized=args.colorized)
     dt = time.perf_counter() - t0
     print(json.dumps({"rank": rank, "world": world, "images": res["images"], "written": len(res["written"]),
                       "errors": res["errors"], "seconds": dt,

@@ -48,14 +48,16 @@ class BatchResult(dict):
 def run_batch(files: Sequence[str], path_out: str, mode: str = "decompose+filter",
               filter_type: str = "bilateral", sigma_color: float = 20.0, sigma_spatial: float = 22.0,
               guidance: Optional[str] = None, iterations: int = 1, device=None, io_threads: int = 8,
-              chunk: int = 16, rank: int = 0, world: int = 1, skip_existing: bool = False) -> BatchResult:
+              chunk: int = 16, rank: int = 0, world: int = 1, skip_existing: bool = False,
+              colorized: bool = False) -> BatchResult:
     """Process ``files`` (this rank's contiguous shard of them).
 
     mode: ``decompose`` (CNN only, writes ``<name>-r.png``), ``filter`` (filter the given images with
     ``guidance``), ``decompose+filter`` (CNN, then filter the reflectance).  guidance: ``None`` = the image
     being filtered guides itself (BF(CNN,CNN)); otherwise a directory holding guidance images with the
     same base names as the inputs.  ``iterations`` > 1 re-applies the filter to its own uint8 output
-    (the "3x GF" configuration); only the final result is written.
+    (the "3x GF" configuration); only the final result is written.  ``colorized``: in the decompose modes
+    also write ``<name>-r_colorized.png`` and ``<name>-s_colorized.png`` as decompose_image does.
     """
     if mode not in ("decompose", "filter", "decompose+filter"):
         raise ValueError("mode must be 'decompose', 'filter' or 'decompose+filter'")
@@ -160,7 +162,11 @@ def run_batch(files: Sequence[str], path_out: str, mode: str = "decompose+filter
                     outs["f"] = filters.replicate_gray_device(g1)
                     cur = None
             else:
-                cur = pipe.reflectance_u8(dimg)  # uint8 [n,h,w]: the bytes of <name>-r.png
+                if colorized:
+                    f32, cur = pipe.net.forward_device(dimg, want_f32=True, want_u8=True)
+                    outs["rc"], outs["sc"] = cnn.colorize_device(dimg, f32)
+                else:
+                    cur = pipe.reflectance_u8(dimg)  # uint8 [n,h,w]: the bytes of <name>-r.png
                 outs["r"] = cur
                 gray = True
             if mode != "decompose" and cur is not None:
@@ -188,6 +194,10 @@ def run_batch(files: Sequence[str], path_out: str, mode: str = "decompose+filter
             r_name, f_name = out_names(f)
             if "r" in host_out:
                 pending_writes.append(pool.submit(save, r_name, host_out["r"][i].numpy()))
+            for key, tail in (("rc", "-r_colorized.png"), ("sc", "-s_colorized.png")):
+                if key in host_out:
+                    pending_writes.append(pool.submit(save, os.path.join(path_out, _stem(f) + tail),
+                                                      host_out[key][i].numpy()))
             if "f" in host_out:
                 pending_writes.append(pool.submit(save, f_name, host_out["f"][i].numpy()))
             res["images"] += 1

@@ -331,14 +331,15 @@ def test_batch_front_end_matches_per_file_cli(tmp_path, net):
     # chain CNN -> BF(CNN, CNN), two shards processed in reverse order
     for rank in (1, 0):
         res = batch.run_batch(files, str(out_a), mode="decompose+filter", filter_type="bilateral", sigma_color=20,
-                              sigma_spatial=22, chunk=2, rank=rank, world=2)
+                              sigma_spatial=22, chunk=2, rank=rank, world=2, colorized=True)
         assert all("broken" in k for k in res["errors"])
     for i in range(5):
         f = str(src_dir / ("im%d.png" % i))
         cnn.decompose_image(f, str(out_b), net=net)
         filters.read_filter_write("bilateral", str(out_b / ("im%d-r.png" % i)), str(out_b / ("im%d-r.png" % i)),
                                   20.0, 22.0, str(out_b))
-        for name in ("im%d-r.png" % i, "im%d-r_bilateral_c20.0s22.0.png" % i):
+        for name in ("im%d-r.png" % i, "im%d-r_bilateral_c20.0s22.0.png" % i, "im%d-r_colorized.png" % i,
+                     "im%d-s_colorized.png" % i):
             a = cv2.imread(str(out_a / name), cv2.IMREAD_UNCHANGED)
             b = cv2.imread(str(out_b / name), cv2.IMREAD_UNCHANGED)
             assert a is not None and a.shape == b.shape and np.array_equal(a, b), name
