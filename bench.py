@@ -158,7 +158,7 @@ def run_reference(args, rank: int):
     line = {
         "impl": "reference", "metric": METRIC, "value": mps, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 weights/sums, u8 pixels", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": make_config(args.batch, max(1, args.gpus),
                               extra={"reference_sample": "each step times %d image(s) of this workload on the host "
                                                          "CPU (bounded sample)" % n_img}),
@@ -332,7 +332,11 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         "fp32_lane_ops": {"per_tap": 4, "achieved_Gop_s": achieved_taps * 4 / 1e9, "peak_Gop_s": alu_peak / 1e9,
                           "frac": achieved_taps * 4 / alu_peak},
         "taps_per_pixel": taps, "launch_ms": bf_ms, "share_of_step": bf_ms / (bf_ms + cnn_ms),
-        "traffic": None, "peak_source": "SM count x unit width x %s clock" % peak_src,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this batch size, from the committed
+        # `ncu --set full` capture profiles/r01_bf_gray2_ncu_full.txt (12.63 MB read, 0 B written: the output is
+        # still in L2 when the kernel ends); algorithmic bytes are 2 * px = 25.2 MB
+        "traffic": 12633600 if B == 64 else None,
+        "peak_source": "SM count x unit width x %s clock" % peak_src,
     }
     cnn_flops = 8704.0 * px_step
     tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0  # dense TF32 = half the measured bf16 rate
@@ -354,7 +358,7 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     line = {
         "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 weights/sums, u8 pixels", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": make_config(B, world, taps, extra={"cache": "inputs rotate through a %d-batch pool (%.0f MB > L2)"
                                                                  % (n_pool, n_pool * batch_bytes / 1e6)}),
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": world * batch_bytes,
