@@ -15,7 +15,9 @@
 //   * the per-row spatial exponents for the four taps of a chunk come from one broadcast LDS.128 of a
 //     table laid out per chunk: (e(qb), e(qb-1), e(qb+1), e(qb)), +inf outside the disc (weight 0).
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -60,7 +62,37 @@ __device__ __forceinline__ float ex2_neg(float x)
     return y;
 }
 
-template <int WY, bool SEP>
+// 2^-a for both halves on the FMA pipe: a = n - g with n = round(a), g in [-0.5, 0.5];
+// 2^g by a degree-5 polynomial (max relative error 2.0e-7 in FP32 Horner form, i.e. as good as MUFU.EX2),
+// 2^-n by subtracting n from the exponent field.  a is clamped to 126, which also maps the +inf of
+// out-of-disc taps to a weight of 2^-126 (1e-38 against a weight sum >= 1).
+__device__ __forceinline__ unsigned long long exp2neg_poly2(unsigned long long a2)
+{
+    float a0, a1;
+    unpack2(a2, a0, a1);
+    const unsigned long long ac = pack2(fminf(a0, 126.0f), fminf(a1, 126.0f));
+    const unsigned long long nm = fadd2(ac, pack2(12582912.0f, 12582912.0f));    // 1.5 * 2^23 + n
+    const unsigned long long nf = fadd2(nm, pack2(-12582912.0f, -12582912.0f));  // n as float
+    const unsigned long long g = ffma2r(ac, pack2(-1.0f, -1.0f), nf);            // n - a
+    unsigned long long p = pack2(0.0013280353741720319f, 0.0013280353741720319f);
+    p = ffma2r(p, g, pack2(0.009675574488937855f, 0.009675574488937855f));
+    p = ffma2r(p, g, pack2(0.05550701171159744f, 0.05550701171159744f));
+    p = ffma2r(p, g, pack2(0.24022118747234344f, 0.24022118747234344f));
+    p = ffma2r(p, g, pack2(0.6931470036506653f, 0.6931470036506653f));
+    p = ffma2r(p, g, pack2(1.0000001192092896f, 1.0000001192092896f));
+    float p0, p1, n0, n1;
+    unpack2(p, p0, p1);
+    unpack2(nm, n0, n1);
+    // the low bits of (1.5 * 2^23 + n) are n; shifting by 23 drops the magic constant entirely
+    const float r0 = __uint_as_float(__float_as_uint(p0) - (__float_as_uint(n0) << 23));
+    const float r1 = __uint_as_float(__float_as_uint(p1) - (__float_as_uint(n1) << 23));
+    return pack2(r0, r1);
+}
+
+// POLY: every POLY-th chunk evaluates the weights of its first neighbour with exp2neg_poly2 instead of
+// MUFU.EX2 (0 = never).  The kernel is bound by the XU pipe (one EX2 per tap) while the FMA pipe is ~60 % busy;
+// moving one pair in ten over (POLY = 5) is the measured optimum.
+template <int WY, bool SEP, int POLY>
 __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
 {
     extern __shared__ __align__(16) float smem_f[];
@@ -111,8 +143,9 @@ __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
         const float2 *jrow = reinterpret_cast<const float2 *>(tj + (ty + dyi) * a.pitch + x0);
         const float2 *srow = reinterpret_cast<const float2 *>(ts + (ty + dyi) * a.pitch + x0);
         const float4 *trow = tab + ady * a.nchunk;
-#pragma unroll 2
-        for (int t = t0; t <= t1; ++t) {
+        // one chunk = neighbours (qb, qb+1) x outputs (p0, p1); USE_POLY is a compile-time choice so the
+        // unrolled groups below are straight-line code
+        auto chunk = [&](int t, auto use_poly) {
             const float2 jn = jrow[t];
             const float2 sn = SEP ? srow[t] : jn;
             const float4 e = trow[t];
@@ -120,9 +153,14 @@ __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
                 const unsigned long long d2 = ffma2r(pack2(jn.x, jn.x), neg1, jc2);
                 const unsigned long long u2 = fmul2(d2, ks2);
                 const unsigned long long a2 = ffma2r(u2, u2, pack2(e.x, e.y));
-                float a0, a1;
-                unpack2(a2, a0, a1);
-                const unsigned long long w = pack2(ex2_neg(a0), ex2_neg(a1));
+                unsigned long long w;
+                if (decltype(use_poly)::value) {
+                    w = exp2neg_poly2(a2);
+                } else {
+                    float a0, a1;
+                    unpack2(a2, a0, a1);
+                    w = pack2(ex2_neg(a0), ex2_neg(a1));
+                }
                 sum2 = ffma2r(pack2(sn.x, sn.x), w, sum2);
                 wsum2 = fadd2(wsum2, w);
             }
@@ -136,7 +174,17 @@ __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
                 sum2 = ffma2r(pack2(sn.y, sn.y), w, sum2);
                 wsum2 = fadd2(wsum2, w);
             }
+        };
+        int t = t0;
+        if (POLY > 0) {
+            // groups of POLY chunks: the first one takes the polynomial path for its first neighbour
+            for (; t + POLY - 1 <= t1; t += POLY) {
+                chunk(t, std::true_type{});
+#pragma unroll
+                for (int u = 1; u < (POLY > 0 ? POLY : 1); ++u) chunk(t + u, std::false_type{});
+            }
         }
+        for (; t <= t1; ++t) chunk(t, std::false_type{});
     }
 
     const int gy = ty0 + ty;
@@ -238,18 +286,31 @@ static size_t smem_bytes(int wy, const Geometry &g, bool sep)
     return tile * (sep ? 2 : 1) + ((size_t)(g.r + 1) * g.nchunk * 4 + (g.r + 1)) * 4;
 }
 
-template <int WY, bool SEP>
+// RF_BF_POLY=<n> overrides how often the polynomial path is used (0 = never); measured on B200 (64x512x384, c20 s22): off 10.27 ms, every 5th chunk 9.87 ms,
+// every 3rd 10.57 ms -- the polynomial's dependent chain and half-rate IMAD/FFMA2 cost more than the pipe model says
+static int poly_every()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RF_BF_POLY");
+        v = e ? atoi(e) : 5;
+        if (v != 0) v = 5;
+    }
+    return v;
+}
+
+template <int WY, bool SEP, int POLY>
 static int launch(const Args &a, size_t smem, cudaStream_t st)
 {
     static bool configured[64] = {};
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(bf_gray2_kernel<WY, SEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RF_CUDA_TRY(cudaFuncSetAttribute(bf_gray2_kernel<WY, SEP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured[dev & 63] = true;
     }
     dim3 grid((a.w + TW - 1) / TW, (a.h + WY - 1) / WY, a.n);
-    bf_gray2_kernel<WY, SEP><<<grid, 32 * WY, smem, st>>>(a);
+    bf_gray2_kernel<WY, SEP, POLY><<<grid, 32 * WY, smem, st>>>(a);
     RF_LAUNCH_CHECK("bf_gray2_kernel");
     return RF_OK;
 }
@@ -282,15 +343,20 @@ int run(const uint8_t *joint, const uint8_t *src, uint8_t *dst, int n, int h, in
     while (wy > 4 && smem_bytes(wy, g, sep) > 100 * 1024) wy >>= 1;
     const size_t smem = smem_bytes(wy, g, sep);
     if (smem > 227 * 1024) return fail(RF_EUNSUPPORTED, "bf_gray2: radius %d needs %zu bytes of shared memory", r, smem);
+#define RF_BF2P(WY, PL) (sep ? launch<WY, true, PL>(a, smem, st) : launch<WY, false, PL>(a, smem, st))
 #define RF_BF2(WY)                                                                            \
     case WY:                                                                                  \
-        return sep ? launch<WY, true>(a, smem, st) : launch<WY, false>(a, smem, st)
+        switch (poly_every()) {                                                               \
+            case 0: return RF_BF2P(WY, 0);                                                    \
+            default: return RF_BF2P(WY, 5);                                                   \
+        }
     switch (wy) {
         RF_BF2(4);
         RF_BF2(8);
         RF_BF2(16);
     }
 #undef RF_BF2
+#undef RF_BF2P
     return fail(RF_EINVAL, "bf_gray2: internal dispatch error");
 }
 
