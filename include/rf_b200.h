@@ -62,7 +62,11 @@ unsigned long long rf_launch_count(void);
 /* ---- CNN (per-pixel MLP with skip concat) --------------------------------------------------
  * params: for each hidden layer W[out][in] row-major then b[out]; then the fusing weights
  *         w[sum(out_i)] (concat order = layer order) and its bias.
- * dims:   n_hidden+1 ints, dims[0] == 3, 1 <= dims[i] <= 64 and a multiple of 4 for i >= 1.
+ * dims:   n_hidden+1 ints, dims[0] == 3, all hidden widths equal and one of 8, 16, 32, 64 (the family
+ *         create_convStaticSkipLayers of the reference's training code produces; the shipped net is 5 x 32),
+ *         1 <= n_hidden <= 8; anything else returns RF_EUNSUPPORTED.  Width 32 runs on the tensor cores
+ *         (tcgen05, 3xTF32 split operands, max abs error ~1e-5 on the reflectance); other widths run the
+ *         exact-FP32 CUDA-core kernel.
  * srgb_lut256: the exact table float32(srgb_to_rgb(v/255.0)), v = 0..255, computed by the host in
  *         float64 as the reference does; NULL lets the library compute it with pow() in double. */
 int rf_cnn_create(const float *params, const int *dims, int n_hidden, const float *srgb_lut256,
