@@ -69,26 +69,23 @@ __device__ __forceinline__ void fill_packed(uint32_t *tile, const uint8_t *img, 
     }
 }
 
-template <int WY>
-__device__ __forceinline__ void fill_float(float *tile, const uint8_t *img, const Args &a, int tx0, int ty0)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rows = rows_of(WY, a.r), cols = TW + 2 * a.rpad;
-    for (int yy = warp; yy < rows; yy += WY) {
-        const int gy = reflect101(ty0 - a.r + yy, a.h);
-        const uint8_t *row = img + (size_t)gy * a.w;
-        float *trow = tile + yy * a.pitch;
-        for (int cc = lane; cc < cols; cc += 32) {
-            const int gx = reflect101(tx0 - a.rpad + cc, a.w);
-            trow[cc] = (float)row[gx];
-        }
-    }
-}
-
 __device__ __forceinline__ void load_table(float *tab_s, const Args &a)
 {
-    const int n = (a.r + 1) * a.tabw + (a.r + 1);
+    const int n = (a.r + 1) * 2 * a.tabw + (a.r + 1);
     for (int i = threadIdx.x; i < n; i += blockDim.x) tab_s[i] = a.tab[i];
+}
+
+__device__ __forceinline__ unsigned long long ffma2r(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float ex2_neg(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(-x));
+    return y;
 }
 
 __device__ __forceinline__ float byte_to_float(uint32_t word, int byte)
@@ -108,7 +105,7 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
     uint32_t *tj = smem;
     uint32_t *ts = SEP ? tj + rows * a.pitch : tj;
     float *tab = reinterpret_cast<float *>(ts + rows * a.pitch);
-    const int *roww4 = reinterpret_cast<const int *>(tab + (a.r + 1) * a.tabw);
+    const int *roww4 = reinterpret_cast<const int *>(tab + (a.r + 1) * 2 * a.tabw);
 
     const int img = blockIdx.z;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * (ROWS_PER_WARP * WY);
@@ -130,39 +127,57 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
         acc23[p] = 0ull;
         jc[p] = tj[(ty + a.r) * a.pitch + a.rpad + x0 + p];
     }
-    const float sc = a.ksqrt, scb = -8388608.0f * a.ksqrt;
+    const unsigned long long sc2 = pack2(a.ksqrt, a.ksqrt);
+    const unsigned long long scb2 = pack2(-8388608.0f * a.ksqrt, -8388608.0f * a.ksqrt);
     const int r = a.r;
     for (int dyi = 0; dyi <= 2 * r; ++dyi) {
         const int ady = dyi < r ? r - dyi : dyi - r;
         const int w4 = roww4[ady];
         const uint32_t *jrow = tj + (ty + dyi) * a.pitch + a.rpad + x0;
         const uint32_t *srow = ts + (ty + dyi) * a.pitch + a.rpad + x0;
-        const float *trow = tab + ady * a.tabw + a.rpad;
+        const float *trowA = tab + ady * 2 * a.tabw + a.rpad;  // E(dx), dx = index - 7 relative to qb
+        const float *trowB = trowA + a.tabw;                   // the same row shifted by one entry
         for (int qb = -w4; qb < P + w4; qb += 4) {
             const uint4 jn = *reinterpret_cast<const uint4 *>(jrow + qb);
             const uint4 sn = SEP ? *reinterpret_cast<const uint4 *>(srow + qb) : jn;
-            const float4 t0 = *reinterpret_cast<const float4 *>(trow + qb);
-            const float4 t1 = *reinterpret_cast<const float4 *>(trow + qb + 4);
-            const float4 t2 = *reinterpret_cast<const float4 *>(trow + qb + 8);
-            const float T[12] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w};
+            const float4 a0 = *reinterpret_cast<const float4 *>(trowA + qb);
+            const float4 a1 = *reinterpret_cast<const float4 *>(trowA + qb + 4);
+            const float4 a2v = *reinterpret_cast<const float4 *>(trowA + qb + 8);
+            const float4 b0 = *reinterpret_cast<const float4 *>(trowB + qb);
+            const float4 b1 = *reinterpret_cast<const float4 *>(trowB + qb + 4);
+            const float4 b2 = *reinterpret_cast<const float4 *>(trowB + qb + 8);
+            const float TA[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2v.x, a2v.y, a2v.z, a2v.w};
+            const float TB[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
             const uint32_t jv[4] = {jn.x, jn.y, jn.z, jn.w};
             const uint32_t sv[4] = {sn.x, sn.y, sn.z, sn.w};
+            unsigned long long bg[4], r1[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const unsigned long long bg = pack2(byte_to_float(sv[j], 0), byte_to_float(sv[j], 1));
-                const unsigned long long r1 = pack2(byte_to_float(sv[j], 2), byte_to_float(sv[j], 3));
+                bg[j] = pack2(byte_to_float(sv[j], 0), byte_to_float(sv[j], 1));
+                r1[j] = pack2(byte_to_float(sv[j], 2), byte_to_float(sv[j], 3));
+            }
+            // taps are paired over two adjacent neighbours (jp, jp+1) of the same output p: their spatial
+            // exponents are adjacent table entries, so the range/space arithmetic is one packed FFMA2 each
+#pragma unroll
+            for (int jp = 0; jp < 4; jp += 2) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    uint32_t d;
-                    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;"
-                        : "=r"(d)
-                        : "r"(jc[p]), "r"(jv[j]), "r"(0x4B000000u));
-                    // d is the float 2^23 + alpha; one FMA gives RN(alpha * sc) exactly as a multiply would
-                    const float u = fmaf(__uint_as_float(d), sc, scb);
-                    const float wgt = ex2_approx(fmaf(-u, u, T[j - p + 7]));
-                    const unsigned long long ww = pack2(wgt, wgt);
-                    ffma2(acc01[p], ww, bg);
-                    ffma2(acc23[p], ww, r1);
+                    uint32_t d0, d1;
+                    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d0) : "r"(jc[p]), "r"(jv[jp]), "r"(0x4B000000u));
+                    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d1) : "r"(jc[p]), "r"(jv[jp + 1]), "r"(0x4B000000u));
+                    // d is the float 2^23 + alpha; the FMA gives RN(alpha * ksqrt) exactly as a multiply would
+                    const unsigned long long u2 = ffma2r(pack2(__uint_as_float(d0), __uint_as_float(d1)), sc2, scb2);
+                    const int i = jp - p + 7;  // table entry of tap (jp, p); tap (jp+1, p) is entry i + 1
+                    const unsigned long long e2 = (i & 1) ? pack2(TB[i - 1], TB[i]) : pack2(TA[i], TA[i + 1]);
+                    const unsigned long long x2 = ffma2r(u2, u2, e2);
+                    float x0f, x1f;
+                    unpack2(x2, x0f, x1f);
+                    const float w0 = ex2_neg(x0f), w1 = ex2_neg(x1f);
+                    const unsigned long long ww0 = pack2(w0, w0), ww1 = pack2(w1, w1);
+                    ffma2(acc01[p], ww0, bg[jp]);
+                    ffma2(acc23[p], ww0, r1[jp]);
+                    ffma2(acc01[p], ww1, bg[jp + 1]);
+                    ffma2(acc23[p], ww1, r1[jp + 1]);
                 }
             }
         }
@@ -183,87 +198,6 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
         if (a.dc == 3) {
             o[1] = sat_u8(__fdiv_rn(s1, ws));
             o[2] = sat_u8(__fdiv_rn(s2, ws));
-        }
-    }
-}
-
-// ---- gray kernel: 1-channel joint and src held as floats ---------------------------------------
-// alpha = scale * |dJ| with scale folded into ksqrt (scale = 3 for replicated gray, 1 for true 1-channel).
-template <int WY, bool SEP>
-__global__ void __launch_bounds__(32 * WY) bf_gray_kernel(const Args a)
-{
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int rows = rows_of(WY, a.r);
-    float *tj = reinterpret_cast<float *>(smem);
-    float *ts = SEP ? tj + rows * a.pitch : tj;
-    float *tab = ts + rows * a.pitch;
-    const int *roww4 = reinterpret_cast<const int *>(tab + (a.r + 1) * a.tabw);
-
-    const int img = blockIdx.z;
-    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * (ROWS_PER_WARP * WY);
-    const size_t npx = (size_t)a.h * a.w;
-    fill_float<WY>(tj, a.joint + img * npx, a, tx0, ty0);
-    if (SEP) fill_float<WY>(ts, a.src + img * npx, a, tx0, ty0);
-    load_table(tab, a);
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x0 = (lane & 3) * P;
-    const int ty = warp * ROWS_PER_WARP + (lane >> 2);
-
-    float sum[P], wsum[P];
-    float jc[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        sum[p] = 0.0f;
-        wsum[p] = 0.0f;
-        jc[p] = tj[(ty + a.r) * a.pitch + a.rpad + x0 + p];
-    }
-    const float sc = a.ksqrt;
-    const int r = a.r;
-    for (int dyi = 0; dyi <= 2 * r; ++dyi) {
-        const int ady = dyi < r ? r - dyi : dyi - r;
-        const int w4 = roww4[ady];
-        const float *jrow = tj + (ty + dyi) * a.pitch + a.rpad + x0;
-        const float *srow = ts + (ty + dyi) * a.pitch + a.rpad + x0;
-        const float *trow = tab + ady * a.tabw + a.rpad;
-        for (int qb = -w4; qb < P + w4; qb += 4) {
-            const float4 jn = *reinterpret_cast<const float4 *>(jrow + qb);
-            const float4 sn = SEP ? *reinterpret_cast<const float4 *>(srow + qb) : jn;
-            const float4 t0 = *reinterpret_cast<const float4 *>(trow + qb);
-            const float4 t1 = *reinterpret_cast<const float4 *>(trow + qb + 4);
-            const float4 t2 = *reinterpret_cast<const float4 *>(trow + qb + 8);
-            const float T[12] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w};
-            const float jv[4] = {jn.x, jn.y, jn.z, jn.w};
-            const float sv[4] = {sn.x, sn.y, sn.z, sn.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    // this path is MUFU-bound (one EX2 per tap), so the plain FFMA + FADD pair costs
-                    // nothing over a packed FFMA2 and needs no (s, 1.0f) register pairs
-                    const float u = (jc[p] - jv[j]) * sc;
-                    const float wgt = ex2_approx(fmaf(-u, u, T[j - p + 7]));
-                    sum[p] = fmaf(wgt, sv[j], sum[p]);
-                    wsum[p] += wgt;
-                }
-            }
-        }
-    }
-
-    const int gy = ty0 + ty;
-    if (gy >= a.h) return;
-    uint8_t *drow = a.dst + (img * npx + (size_t)gy * a.w) * a.dc;
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        const int gx = tx0 + x0 + p;
-        if (gx >= a.w) break;
-        const uint8_t v = sat_u8(__fdiv_rn(sum[p], wsum[p]));
-        uint8_t *o = drow + (size_t)gx * a.dc;
-        o[0] = v;
-        if (a.dc == 3) {
-            o[1] = v;
-            o[2] = v;
         }
     }
 }
@@ -301,8 +235,10 @@ struct TableEntry {
 static std::mutex g_tab_mu;
 static std::vector<TableEntry> g_tabs;
 
-// exponent table in the log2 domain: tab[ady][i] = (dx^2 + ady^2) * (-0.5 / sigma_space^2) * log2(e),
-// dx = i - rpad - 7, or -inf outside the disc; followed by ceil4(half width) per |dy|.
+// exponent table in the log2 domain, two copies per |dy| row:
+//   A[ady][i] = (dx^2 + ady^2) * 0.5 / sigma_space^2 * log2(e), dx = i - rpad - 7, +inf outside the disc
+//   B[ady][i] = A[ady][i + 1]   (so that any two adjacent entries are an aligned register pair in A or in B)
+// followed by ceil4(half width) per |dy|.  The weight of a tap is exp2(-(alpha*ksqrt)^2 - A).
 static int get_table(double sigma_space, const Geometry &g, const float **out)
 {
     int dev = 0;
@@ -313,18 +249,21 @@ static int get_table(double sigma_space, const Geometry &g, const float **out)
             *out = e.d_tab;
             return RF_OK;
         }
-    const int n = (g.r + 1) * g.tabw + (g.r + 1);
+    const int n = (g.r + 1) * 2 * g.tabw + (g.r + 1);
     std::vector<float> h(n);
-    const double gsc = -0.5 / (sigma_space * sigma_space) * 1.4426950408889634074;
+    const double gsc = 0.5 / (sigma_space * sigma_space) * 1.4426950408889634074;
+    auto E = [&](int i, int ady) -> float {
+        const int dx = i - g.rpad - 7;
+        const int d2 = dx * dx + ady * ady;
+        return (i < g.tabw && d2 <= g.r * g.r) ? (float)(d2 * gsc) : INFINITY;
+    };
     for (int ady = 0; ady <= g.r; ++ady) {
         for (int i = 0; i < g.tabw; ++i) {
-            const int dx = i - g.rpad - 7;
-            const int d2 = dx * dx + ady * ady;
-            h[ady * g.tabw + i] = d2 <= g.r * g.r ? (float)(d2 * gsc) : -INFINITY;
+            h[(size_t)ady * 2 * g.tabw + i] = E(i, ady);
+            h[(size_t)ady * 2 * g.tabw + g.tabw + i] = E(i + 1, ady);
         }
         const int hw = (int)std::floor(std::sqrt((double)(g.r * g.r - ady * ady)));
-        int w4 = ceil4(hw);
-        reinterpret_cast<int *>(h.data())[(g.r + 1) * g.tabw + ady] = w4;
+        reinterpret_cast<int *>(h.data())[(g.r + 1) * 2 * g.tabw + ady] = ceil4(hw);
     }
     float *d = nullptr;
     RF_CUDA_TRY(cudaMalloc(&d, n * sizeof(float)));
@@ -345,7 +284,7 @@ static int get_table(double sigma_space, const Geometry &g, const float **out)
 static size_t smem_bytes(int wy, const Geometry &g, bool sep)
 {
     const size_t tile = (size_t)rows_of(wy, g.r) * g.pitch * 4;
-    return tile * (sep ? 2 : 1) + ((size_t)(g.r + 1) * g.tabw + (g.r + 1)) * 4;
+    return tile * (sep ? 2 : 1) + ((size_t)(g.r + 1) * 2 * g.tabw + (g.r + 1)) * 4;
 }
 
 template <typename K>
@@ -374,13 +313,21 @@ static int launch(K kernel, int wy, const Args &a, size_t smem, cudaStream_t st,
 
 static int pick_wy(const Args &a, const Geometry &g, bool sep)
 {
-    // Larger CTAs amortise the window fill; smaller ones balance a small grid over 148 SMs.
+    // Tall CTAs (32 x 8*WY pixels) amortise the halo and the exponent table, which is what lets enough warps
+    // share an SM (ncu: 12 resident warps left every pipe below 70 %); small grids need small CTAs to spread
+    // over the 148 SMs.
     const long warp_tiles = (long)((a.w + TW - 1) / TW) * ((a.h + ROWS_PER_WARP - 1) / ROWS_PER_WARP) * a.n;
     const long sms = sm_count();
-    int wy = 4;
-    if (warp_tiles < sms * 4 * 8) wy = 2;
-    if (warp_tiles < sms * 2 * 8) wy = 1;
-    while (wy > 1 && smem_bytes(wy, g, sep) > 200 * 1024) wy >>= 1;
+    int wy = 16;
+    if (warp_tiles < sms * 16 * 4) wy = 8;
+    if (warp_tiles < sms * 8 * 4) wy = 4;
+    if (warp_tiles < sms * 4 * 4) wy = 2;
+    if (warp_tiles < sms * 2 * 4) wy = 1;
+    // two CTAs per SM when possible, never more than the 227 KB limit
+    while (wy > 1 && smem_bytes(wy, g, sep) > 113 * 1024 && smem_bytes(wy / 2, g, sep) * 2 <= 227 * 1024 &&
+           smem_bytes(wy, g, sep) > 227 * 1024 / 2)
+        wy >>= 1;
+    while (wy > 1 && smem_bytes(wy, g, sep) > 227 * 1024) wy >>= 1;
     return wy;
 }
 
@@ -395,17 +342,6 @@ int run(const uint8_t *joint, const uint8_t *src, uint8_t *dst, int n, int h, in
 }  // namespace rf
 
 using namespace rf;
-
-// RF_BF_V1=1 keeps the first-generation gray kernel (used to cross-check the two implementations)
-static bool use_v1_gray()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("RF_BF_V1");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
 
 extern "C" int rf_joint_bilateral_max_radius(void) { return bf::MAX_RADIUS; }
 
@@ -460,26 +396,10 @@ extern "C" int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t
     cudaStream_t st = (cudaStream_t)stream;
     const double ksq = std::sqrt(0.5 / (sigma_color * sigma_color) * 1.4426950408889634074);
     const bool gray = (jc == 1 && sc == 1);
-    if (gray && !use_v1_gray())
+    if (gray)
         return bf2::run(joint, src, dst, n, h, w, g.r, sigma_color, sigma_space, gray_rep ? 3.0 : 1.0,
                         (cudaStream_t)stream);
-    if (gray) {
-        const double scale = gray_rep ? 3.0 : 1.0;
-        a.ksqrt = (float)(ksq * scale);
-        a.dc = 1;
-        const int wy = bf::pick_wy(a, g, sep);
-        const size_t smem = bf::smem_bytes(wy, g, sep);
-#define RF_BF_GRAY(WY)                                                                                   \
-    case WY:                                                                                             \
-        return sep ? bf::launch(bf::bf_gray_kernel<WY, true>, WY, a, smem, st, "bf_gray_kernel")         \
-                   : bf::launch(bf::bf_gray_kernel<WY, false>, WY, a, smem, st, "bf_gray_kernel")
-        switch (wy) {
-            RF_BF_GRAY(1);
-            RF_BF_GRAY(2);
-            RF_BF_GRAY(4);
-        }
-#undef RF_BF_GRAY
-    } else {
+    {
         a.ksqrt = (float)ksq;
         const int wy = bf::pick_wy(a, g, sep);
         const size_t smem = bf::smem_bytes(wy, g, sep);
@@ -491,6 +411,8 @@ extern "C" int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t
             RF_BF_COLOR(1);
             RF_BF_COLOR(2);
             RF_BF_COLOR(4);
+            RF_BF_COLOR(8);
+            RF_BF_COLOR(16);
         }
 #undef RF_BF_COLOR
     }
