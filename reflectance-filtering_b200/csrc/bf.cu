@@ -313,22 +313,31 @@ static int launch(K kernel, int wy, const Args &a, size_t smem, cudaStream_t st,
 
 static int pick_wy(const Args &a, const Geometry &g, bool sep)
 {
-    // Tall CTAs (32 x 8*WY pixels) amortise the halo and the exponent table, which is what lets enough warps
-    // share an SM (ncu: 12 resident warps left every pipe below 70 %); small grids need small CTAs to spread
-    // over the 148 SMs.
-    const long warp_tiles = (long)((a.w + TW - 1) / TW) * ((a.h + ROWS_PER_WARP - 1) / ROWS_PER_WARP) * a.n;
+    // CTA = 32 x 8*WY pixels.  A warp's work is fixed (32 x 8 pixels), an SM runs its resident warps concurrently
+    // and saturates at about a dozen of them, and shared memory (window + tables) decides how many CTAs fit.
+    // Cost model: waves x max(1, resident warps / 12); ties go to the variant with more resident warps
+    // (tall CTAs amortise the halo), then to the one that spreads over more SMs.
     const long sms = sm_count();
-    int wy = 16;
-    if (warp_tiles < sms * 16 * 4) wy = 8;
-    if (warp_tiles < sms * 8 * 4) wy = 4;
-    if (warp_tiles < sms * 4 * 4) wy = 2;
-    if (warp_tiles < sms * 2 * 4) wy = 1;
-    // two CTAs per SM when possible, never more than the 227 KB limit
-    while (wy > 1 && smem_bytes(wy, g, sep) > 113 * 1024 && smem_bytes(wy / 2, g, sep) * 2 <= 227 * 1024 &&
-           smem_bytes(wy, g, sep) > 227 * 1024 / 2)
-        wy >>= 1;
-    while (wy > 1 && smem_bytes(wy, g, sep) > 227 * 1024) wy >>= 1;
-    return wy;
+    const long cols = (a.w + TW - 1) / TW;
+    int best = 1;
+    double best_cost = 1e30;
+    long best_warps = 0;
+    for (int wy = 1; wy <= 16; wy <<= 1) {
+        const size_t smem = smem_bytes(wy, g, sep);
+        if (smem > 227 * 1024) break;
+        long res = (long)((227 * 1024) / smem);
+        if (res * wy > 48) res = 48 / wy > 0 ? 48 / wy : 1;
+        const long ctas = cols * ((a.h + ROWS_PER_WARP * wy - 1) / (ROWS_PER_WARP * wy)) * a.n;
+        const long waves = (ctas + sms * res - 1) / (sms * res);
+        const long resident = res * wy < (ctas * wy + sms - 1) / sms ? res * wy : (ctas * wy + sms - 1) / sms;
+        const double cost = (double)waves * (resident > 12 ? resident / 12.0 : 1.0);
+        if (cost < best_cost * 0.97 || (cost < best_cost * 1.03 && resident > best_warps)) {
+            best_cost = cost < best_cost ? cost : best_cost;
+            best_warps = resident;
+            best = wy;
+        }
+    }
+    return best;
 }
 
 }  // namespace bf
