@@ -14,6 +14,8 @@
  *                                       sigmaSpace)        filter_reflectance.py:60-64
  *   rf_guided_u8                        cv2.ximgproc.guidedFilter(guide, src, radius, eps)
  *                                                          filter_reflectance.py:67-70
+ *   rf_whdr_f32                         whdr(reflectance, comparisons, delta)
+ *                                                          training/layers/whdr_layer.py:253-287
  *   rf_colorize_u8                      image_utils.colorize / normalize / rgb_to_srgb / imwrite
  *                                       quantisation       image_utils.py:42-49,60-92
  *
@@ -121,6 +123,19 @@ size_t rf_colorize_workspace_bytes(int n, int h, int w);
 int rf_colorize_u8(const uint8_t *bgr, const float *intensity, int n, int h, int w, double eps,
                    unsigned long long k_reflectance, unsigned long long k_shading, uint8_t *out_reflectance,
                    uint8_t *out_shading, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- WHDR of reflectance images (training/layers/whdr_layer.py:253-287) ---------------------
+ * reflectance: float [n][c][h][w] (planar, c in {1, 3}; the CNN's out_f32 is the c = 1 case).
+ * comparisons: float64 [n][max_comparisons + 1][6], the blob of createNumpyArrayWithComparisonsForIIW.py:616-649:
+ *   row i < count = (x1, y1, x2, y2, darker, weight), darker 0 = equal / 1 / 2; last row = (count, file name, 0).
+ *   Coordinates are relative ([0,1), scaled as int(x * w), int(y * h) like whdr_layer.py:240-251) unless
+ *   RF_WHDR_PIXEL_COORDS is set (already-scaled values, what whdr() itself receives).
+ * out_sums: device float64 [n][2] = (error_sum, weight_sum) per image; WHDR = error_sum / weight_sum, 0 if the
+ *   weight sum is 0.  bad_flag: device int, OR-ed with 1 for an invalid count row, 2 for a coordinate outside the
+ *   image (numpy raises IndexError there; such comparisons are skipped); never cleared by this call. */
+#define RF_WHDR_PIXEL_COORDS 1u
+int rf_whdr_f32(const float *reflectance, int c, int n, int h, int w, const double *comparisons,
+                int max_comparisons, double delta, unsigned flags, double *out_sums, int *bad_flag, void *stream);
 
 /* ---- aggregate statistics (the one value a multi-GPU run may all-reduce) --------------------
  * stats[0] += n_px ; [1] += sum(out) ; [2] += sum(out^2) ; [3] += sum|out - in| ; device doubles */

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "librf_b200.so")
 
 RF_OK, RF_EINVAL, RF_EUNSUPPORTED, RF_ECUDA, RF_ENOMEM = 0, 1, 2, 3, 4
 RF_BF_GRAY_REPLICATED = 1
+RF_WHDR_PIXEL_COORDS = 1
 
 _lib = None
 
@@ -38,6 +39,7 @@ SIGNATURES = {
     "rf_replicate_gray_u8": (_i, [_vp, _vp, _sz, _vp]),
     "rf_extract_gray_u8": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "rf_accumulate_stats_u8": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "rf_whdr_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _d, _u, _vp, _vp, _vp]),
     "rf_colorize_workspace_bytes": (_sz, [_i, _i, _i]),
     "rf_colorize_u8": (_i, [_vp, _vp, _i, _i, _i, _d, C.c_ulonglong, C.c_ulonglong, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -67,3 +67,19 @@ def batch(kind: str, n: int, h: int, w: int, config_id: int, start: int = 0) -> 
     """``uint8[n,h,w,3]`` with per-image seeds ``1000*config_id + start + i``."""
     gen = GENERATORS[kind]
     return np.stack([gen(h, w, 1000 * config_id + start + i) for i in range(n)])
+
+
+def comparisons(n: int, max_comparisons: int, seed: int, min_count: int = 0) -> np.ndarray:
+    """Synthetic IIW-style comparison blobs ``[n, max_comparisons + 1, 1, 6]`` float64 in the layout of the
+    reference's createNumpyArrayWithComparisonsForIIW.py:616-649: rows ``(x1, y1, x2, y2, darker, weight)`` with
+    relative coordinates in [0, 1), darker in {0, 1, 2}, weights in (0, 3]; NaN padding; the last row holds
+    ``(count, file name, 0)``.  (The IIW judgements themselves are not available offline.)"""
+    rng = np.random.default_rng(seed)
+    blob = np.full((n, max_comparisons + 1, 1, 6), np.nan)
+    for i in range(n):
+        count = int(rng.integers(min_count, max_comparisons + 1))
+        blob[i, :count, 0, 0:4] = rng.uniform(0.0, 1.0, (count, 4)) * (1.0 - 1e-9)
+        blob[i, :count, 0, 4] = rng.integers(0, 3, count)
+        blob[i, :count, 0, 5] = rng.uniform(0.05, 3.0, count)
+        blob[i, max_comparisons, 0, 0:3] = (count, float(100000 + i), 0.0)
+    return blob

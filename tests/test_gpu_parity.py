@@ -355,6 +355,41 @@ def test_batch_front_end_matches_per_file_cli(tmp_path, net):
     assert np.array_equal(cv2.imread(str(out_a / "im2_guided_c3.0s7.0.png")), cur)
 
 
+def test_whdr_matches_reference_golden_and_oracle(golden_dir, net):
+    """rf_whdr_f32 against the reference's own whdr() (golden_whdr.npz) and the restatement on CNN output."""
+    from reflectance_filtering_b200 import whdr
+    W = np.load(os.path.join(golden_dir, "golden_whdr.npz"))
+    for case in W["cases"]:
+        refl, blob, delta = W[case + "_reflectance"], W[case + "_blob"], float(W[case + "_delta"])
+        got = whdr.whdr_device(torch.from_numpy(refl).cuda(), torch.from_numpy(blob).cuda(), delta).cpu().numpy()
+        np.testing.assert_allclose(got, W[case + "_whdr"], rtol=0, atol=1e-13)   # float64 tree sum vs sequential
+        assert got[0] == 0.0
+        # the numpy-facing mirror of whdr(reflectance, comparisons, delta) with pixel coordinates
+        comps, _ = whdr.get_comparisons_from_blob(blob[1], refl.shape[2], refl.shape[3], delta)
+        assert abs(whdr.whdr(refl[1], comps, delta) - W[case + "_whdr"][1]) < 1e-13
+    # on the CNN's own output: [n, h, w] float32 straight from forward_device
+    imgs = synth.batch("natural", 4, 96, 128, 31)
+    r = net.forward_device(dev_u8(imgs), want_f32=True, want_u8=False)[0]
+    blob = synth.comparisons(4, 1181, seed=9, min_count=500)
+    got = whdr.whdr_device(r, torch.from_numpy(blob).cuda(), 0.1).cpu().numpy()
+    rh = r.cpu().numpy()
+    want = np.array([oracle.whdr(rh[b][None], blob[b], 0.1) for b in range(4)])
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
+    mean, count = whdr.mean_whdr(r, torch.from_numpy(blob).cuda(), 0.1)
+    assert count == 4 and abs(mean - want.mean()) < 1e-13
+    # error behaviour: coordinate outside the image -> IndexError (numpy's), broken count row -> ValueError
+    bad = blob.copy()
+    bad[0, 0, 0, 0] = 1.0
+    with pytest.raises(IndexError):
+        whdr.whdr_device(r, torch.from_numpy(bad).cuda(), 0.1)
+    bad = blob.copy()
+    bad[2, -1, 0, 0] = np.nan
+    with pytest.raises(ValueError):
+        whdr.whdr_device(r, torch.from_numpy(bad).cuda(), 0.1)
+    with pytest.raises(Exception, match="Expecting 1 or 3 channels"):
+        whdr.whdr_device(torch.zeros(1, 2, 4, 4, device="cuda"), torch.from_numpy(blob[:1]).cuda(), 0.1)
+
+
 def test_native_library_is_the_one_loaded():
     from reflectance_filtering_b200 import _native
     before = _native.launch_count()

@@ -229,6 +229,11 @@ dist.all_reduce(chk)   # the only collective a run needs: aggregate statistics
 full = synth.batch("stress", n, 8, 12, 9)
 assert chk[1].item() == n and chk[0].item() == float(full.astype(np.float64).sum()), chk
 assert np.array_equal(mine, full[lo:hi])
+# mean WHDR over all ranks' images (whdr.reduce_mean): shards of unequal size, weighted by image count
+from reflectance_filtering_b200 import whdr
+vals = torch.arange(1, n + 1, dtype=torch.float64) / 10.0
+mean, count = whdr.reduce_mean(vals[lo:hi])
+assert count == n and abs(mean - float(vals.mean())) < 1e-15, (mean, count)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
@@ -243,3 +248,20 @@ def test_sharding_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_whdr_host_helpers():
+    """Blob layout and the host-side view of the comparisons (no device needed)."""
+    from reflectance_filtering_b200 import whdr
+    blob = synth.comparisons(3, 50, seed=5, min_count=10)
+    assert blob.shape == (3, 51, 1, 6) and blob.dtype == np.float64
+    for b in range(3):
+        count = int(blob[b, -1, 0, 0])
+        assert 10 <= count <= 50 and np.isnan(blob[b, count:50]).all() and np.isfinite(blob[b, :count]).all()
+        comps, name = whdr.get_comparisons_from_blob(blob[b], 30, 40, 0.1)
+        assert comps.shape == (count, 6) and name == 100000 + b
+        assert (comps[:, [0, 2]] < 40).all() and (comps[:, [1, 3]] < 30).all() and (comps[:, :4] == np.floor(comps[:, :4])).all()
+    import torch
+    mean, count = whdr.reduce_mean(torch.tensor([0.2, 0.4], dtype=torch.float64))
+    assert count == 2 and abs(mean - 0.3) < 1e-15
+    assert whdr.reduce_mean(torch.zeros(0, dtype=torch.float64)) == (0.0, 0)

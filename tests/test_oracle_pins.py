@@ -3,6 +3,8 @@
 Fixtures in tests/golden/golden.npz come from the reference's own image_utils.py and from
 cv2.dnn / cv2.bilateralFilter / cv2.boxFilter (tests/golden/make_golden.py).  Runs without a GPU.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -143,3 +145,13 @@ def test_apply_filter_errors_match_reference(golden_dir):
         with pytest.raises(ValueError) as ei:
             oracle.apply_filter(ftype, z, z, float(sc), float(ss))
         assert exc == "ValueError" and str(ei.value) == msg
+
+
+def test_whdr_restatement_matches_reference_code(golden_dir):
+    """golden_whdr.npz was produced by the reference's own whdr() (tests/golden/make_golden_whdr.py)."""
+    W = np.load(os.path.join(golden_dir, "golden_whdr.npz"))
+    for case in W["cases"]:
+        refl, blob, delta = W[case + "_reflectance"], W[case + "_blob"], float(W[case + "_delta"])
+        got = np.array([oracle.whdr(refl[b], blob[b], delta) for b in range(refl.shape[0])])
+        np.testing.assert_array_equal(got, W[case + "_whdr"])
+        assert got[0] == 0.0 and (got[1:] > 0).all()
