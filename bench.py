@@ -305,7 +305,15 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
             gev[i + 1].record()
         barrier()
         gf_iter_ms = float(np.mean([gev[i].elapsed_time(gev[i + 1]) for i in range(g_steps)]))
-        gf = {"ms_per_step": gf_ms, "gf_iteration_ms": gf_iter_ms, "batch": GB, "steps": g_steps}
+        # the three iterations as one call (rf_guided_iterated_u8: guide statistics computed once)
+        barrier()
+        gev[0].record()
+        for i in range(g_steps):
+            tmp = filters.guided_device(d_flat, r8, 45, 3.0, out=tmp, iterations=3)
+            gev[i + 1].record()
+        barrier()
+        gf_x3_ms = float(np.mean([gev[i].elapsed_time(gev[i + 1]) for i in range(g_steps)]))
+        gf = {"ms_per_step": gf_ms, "gf_iteration_ms": gf_iter_ms, "gf_x3_ms": gf_x3_ms, "batch": GB, "steps": g_steps}
 
     if rank != 0:
         if world > 1:
@@ -377,14 +385,18 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         # algorithmic bytes per pixel per iteration, 1-channel src: pass A reads 3 (guide)
         # + 1 (src) and writes 16 (a0,a1,a2,b); pass B reads 16 + 3 (guide) and writes 1  => 40 B/px
         bpp = 40.0
-        ach = gpx * bpp / (gf["gf_iteration_ms"] * 1e-3) / 1e9
+        ach = gpx * bpp * 3 / (gf["gf_x3_ms"] * 1e-3) / 1e9
         line["config3_cnn_gf_x3"] = {
             "workload": "configs[2]: %d x 512x384, CNN -> GF(CNN, flat guide) c3.0 s45.0 (r=45), 3 iterations, "
                         "uint8 re-quantisation between iterations" % gf["batch"],
             "value": world * gpx / (gf["ms_per_step"] * 1e-3) / 1e6, "unit": "MP/s", "ms_per_step": gf["ms_per_step"],
-            "roofline": {"kernel": "gf2 pack + pass_a<1> + pass_b<1> (one iteration)", "bound": "hbm", "achieved": ach,
-                         "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "bytes_per_pixel": bpp,
-                         "launch_ms": gf["gf_iteration_ms"], "traffic": None, "peak_source": peak_src}}
+            "roofline": {"kernel": "rf_guided_iterated_u8, 3 iterations: gf2 pack + pass_a<full+stats> + pass_b, then "
+                                   "2 x (pass_a<source only> + pass_b)", "bound": "hbm", "achieved": ach,
+                         "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "bytes_per_pixel_per_iteration": bpp,
+                         "launch_ms": gf["gf_x3_ms"], "single_iteration_call_ms": gf["gf_iteration_ms"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the seven launches at batch 64, from
+                         # profiles/r01_gf3_ncu_full.txt (algorithmic: 3 x 40 B x 12.58 Mpx = 1.51 GB)
+                         "traffic": 5150000000 if gf["batch"] == 64 else None, "peak_source": peak_src}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

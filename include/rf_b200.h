@@ -103,6 +103,15 @@ size_t rf_guided_workspace_bytes(int sc, int n, int h, int w, int radius);
 int rf_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst, int n,
                  int h, int w, int radius, double eps, void *ws, size_t ws_bytes, void *stream);
 int rf_guided_max_radius(void);
+/* The same guide applied `iterations` times: iteration k filters the uint8 output of iteration k-1
+ * (createGuidedFilter(guide, radius, eps) reused for several ->filter() calls; the reference's "3 x GF"
+ * setting re-runs filter_reflectance.py on its own output).  Byte-identical to `iterations` calls of
+ * rf_guided_u8; the guide statistics (mean I, inverse of cov(I) + eps*Id) are computed once and kept in
+ * the workspace. */
+size_t rf_guided_iterated_workspace_bytes(int sc, int n, int h, int w, int radius, int iterations);
+int rf_guided_iterated_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst, int n,
+                          int h, int w, int radius, double eps, int iterations, void *ws, size_t ws_bytes,
+                          void *stream);
 
 /* ---- layout helpers ------------------------------------------------------------------------ */
 /* gray [n_px] -> bgr [n_px][3] with three equal channels (what cv2.imread returns for the CNN PNG) */

@@ -36,6 +36,8 @@ SIGNATURES = {
     "rf_guided_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rf_guided_u8": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
     "rf_guided_max_radius": (_i, []),
+    "rf_guided_iterated_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "rf_guided_iterated_u8": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _d, _i, _vp, _sz, _vp]),
     "rf_replicate_gray_u8": (_i, [_vp, _vp, _sz, _vp]),
     "rf_extract_gray_u8": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "rf_accumulate_stats_u8": (_i, [_vp, _vp, _sz, _vp, _vp]),

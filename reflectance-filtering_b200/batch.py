@@ -170,7 +170,10 @@ def run_batch(files: Sequence[str], path_out: str, mode: str = "decompose+filter
                 outs["r"] = cur
                 gray = True
             if mode != "decompose" and cur is not None:
-                for _ in range(max(1, iterations)):
+                fixed_guide = filter_type == "guided" and dgd is not None
+                if fixed_guide:  # one guide for every iteration: its statistics are computed once
+                    cur = filters.guided_device(dgd, cur, int(sigma_spatial), sigma_color, iterations=max(1, iterations))
+                for _ in range(0 if fixed_guide else max(1, iterations)):
                     if filter_type == "bilateral":
                         if gray and dgd is None:
                             cur = filters.joint_bilateral_device(cur, cur, sigma_color, sigma_spatial, gray_replicated=True)
@@ -179,7 +182,7 @@ def run_batch(files: Sequence[str], path_out: str, mode: str = "decompose+filter
                             jnt = dgd if dgd is not None else src3
                             cur, gray = filters.joint_bilateral_device(jnt, src3, sigma_color, sigma_spatial), False
                     else:
-                        guide = dgd if dgd is not None else (filters.replicate_gray_device(cur) if gray else cur)
+                        guide = filters.replicate_gray_device(cur) if gray else cur  # the image guides itself
                         cur = filters.guided_device(guide, cur, int(sigma_spatial), sigma_color)
                 outs["f"] = filters.replicate_gray_device(cur) if gray else cur  # what cv2.imwrite gets
             host_out = {k: pin("out_" + k, v.shape, slot) for k, v in outs.items()}

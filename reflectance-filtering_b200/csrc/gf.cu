@@ -315,36 +315,13 @@ static int run(Args a, cudaStream_t st)
 namespace rf {
 namespace gf2 {  // gf2.cu: strip kernels for radius <= 64
 bool supported(int r, int h, int w);
-size_t workspace_per_image(int sc, int h, int w, int r);
+size_t workspace_per_image(int sc, int h, int w, int r, int iterations);
 int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws, int n, int h, int w, int r,
-        double eps, cudaStream_t st);
+        double eps, int iterations, cudaStream_t st);
 }  // namespace gf2
 }  // namespace rf
 
 using namespace rf;
-
-static size_t per_image_bytes(int sc, int h, int w, int radius)
-{
-    size_t per = gf::per_image_ws(sc, h, w);
-    if (gf2::supported(radius, h, w)) {
-        const size_t p2 = gf2::workspace_per_image(sc, h, w, radius);
-        if (p2 > per) per = p2;
-    }
-    return per;
-}
-
-extern "C" int rf_guided_max_radius(void) { return gf::MAX_RADIUS; }
-
-extern "C" size_t rf_guided_workspace_bytes(int sc, int n, int h, int w, int radius)
-{
-    if (!(sc == 1 || sc == 3) || n < 1 || h < 1 || w < 1) return 0;
-    // the call processes the batch in chunks if given less; never ask for more than 8 GiB
-    const size_t per = per_image_bytes(sc, h, w, radius);
-    size_t want = per * (size_t)n;
-    const size_t cap = (size_t)8 << 30;
-    if (want > cap) want = (cap / per > 0 ? cap / per : 1) * per;
-    return want;
-}
 
 // RF_GF_GENERIC=1 in the environment forces the generic (any radius, FP64 box mean) kernels: used by the
 // tests to cross-check the two implementations against each other.
@@ -358,21 +335,45 @@ static int flags_generic_path()
     return v;
 }
 
-extern "C" int rf_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst, int n, int h,
-                            int w, int radius, double eps, void *ws, size_t ws_bytes, void *stream)
+// workspace one image needs: the larger of the two implementations' planes; iterated calls add the guide
+// statistics (fast path) or one uint8 image to ping-pong through (generic path)
+static size_t per_image_bytes(int sc, int h, int w, int radius, int iterations)
 {
-    if (!guide || !src || !dst || !ws) return fail(RF_EINVAL, "rf_guided_u8: NULL pointer");
-    if (gc != 3) return fail(RF_EUNSUPPORTED, "rf_guided_u8: only 3-channel guides are supported (got %d)", gc);
-    if (!(sc == 1 || sc == 3)) return fail(RF_EINVAL, "rf_guided_u8: src channels must be 1 or 3 (got %d)", sc);
-    if (n < 0 || h < 1 || w < 1) return fail(RF_EINVAL, "rf_guided_u8: bad shape n=%d h=%d w=%d", n, h, w);
-    if (radius < 0) return fail(RF_EINVAL, "rf_guided_u8: negative radius");
+    size_t per = gf::per_image_ws(sc, h, w) + (iterations > 1 ? (((size_t)h * w * sc + 15) & ~(size_t)15) : 0);
+    if (gf2::supported(radius, h, w)) {
+        const size_t p2 = gf2::workspace_per_image(sc, h, w, radius, iterations);
+        if (p2 > per) per = p2;
+    }
+    return per;
+}
+
+static size_t workspace_bytes(int sc, int n, int h, int w, int radius, int iterations)
+{
+    if (!(sc == 1 || sc == 3) || n < 1 || h < 1 || w < 1 || iterations < 1) return 0;
+    // the call processes the batch in chunks if given less; never ask for more than 8 GiB
+    const size_t per = per_image_bytes(sc, h, w, radius, iterations);
+    size_t want = per * (size_t)n;
+    const size_t cap = (size_t)8 << 30;
+    if (want > cap) want = (cap / per > 0 ? cap / per : 1) * per;
+    return want;
+}
+
+static int guided_impl(const char *fn, const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst, int n,
+                       int h, int w, int radius, double eps, int iterations, void *ws, size_t ws_bytes, void *stream)
+{
+    if (!guide || !src || !dst || !ws) return fail(RF_EINVAL, "%s: NULL pointer", fn);
+    if (gc != 3) return fail(RF_EUNSUPPORTED, "%s: only 3-channel guides are supported (got %d)", fn, gc);
+    if (!(sc == 1 || sc == 3)) return fail(RF_EINVAL, "%s: src channels must be 1 or 3 (got %d)", fn, sc);
+    if (n < 0 || h < 1 || w < 1) return fail(RF_EINVAL, "%s: bad shape n=%d h=%d w=%d", fn, n, h, w);
+    if (radius < 0) return fail(RF_EINVAL, "%s: negative radius", fn);
+    if (iterations < 1) return fail(RF_EINVAL, "%s: iterations must be >= 1", fn);
     if (radius > gf::MAX_RADIUS)
-        return fail(RF_EUNSUPPORTED, "rf_guided_u8: radius %d exceeds the supported maximum %d", radius, gf::MAX_RADIUS);
+        return fail(RF_EUNSUPPORTED, "%s: radius %d exceeds the supported maximum %d", fn, radius, gf::MAX_RADIUS);
     if (n == 0) return RF_OK;
-    if (dst == src || dst == guide) return fail(RF_EINVAL, "rf_guided_u8: dst must not alias an input");
-    const size_t per = per_image_bytes(sc, h, w, radius);
-    if (ws_bytes < per) return fail(RF_EINVAL, "rf_guided_u8: workspace too small (%zu < %zu bytes)", ws_bytes, per);
-    if ((uintptr_t)ws % 16) return fail(RF_EINVAL, "rf_guided_u8: workspace must be 16-byte aligned");
+    if (dst == src || dst == guide) return fail(RF_EINVAL, "%s: dst must not alias an input", fn);
+    const size_t per = per_image_bytes(sc, h, w, radius, iterations);
+    if (ws_bytes < per) return fail(RF_EINVAL, "%s: workspace too small (%zu < %zu bytes)", fn, ws_bytes, per);
+    if ((uintptr_t)ws % 16) return fail(RF_EINVAL, "%s: workspace must be 16-byte aligned", fn);
     const int k = 2 * radius + 1;
     int chunk = (int)(ws_bytes / per < (size_t)n ? ws_bytes / per : (size_t)n);
     if (chunk > 65535) chunk = 65535;
@@ -382,25 +383,59 @@ extern "C" int rf_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, in
         const int nn = n - i0 < chunk ? n - i0 : chunk;
         if (!generic) {
             int rc = gf2::run(guide + i0 * img_px * 3, src + i0 * img_px * sc, sc, dst + i0 * img_px * sc, ws, nn, h, w,
-                              radius, eps, (cudaStream_t)stream);
+                              radius, eps, iterations, (cudaStream_t)stream);
             if (rc != RF_OK) return rc;
             continue;
         }
-        gf::Args a;
-        a.n = nn;
-        a.guide = guide + i0 * img_px * 3;
-        a.src = src + i0 * img_px * sc;
-        a.dst = dst + i0 * img_px * sc;
-        a.ab = (float4 *)ws;
-        a.h = h;
-        a.w = w;
-        a.r = radius;
-        a.eps = (float)eps;
-        a.scale = 1.0 / ((double)k * k);
-        a.twa = 0;
-        a.seg_rows = 0;
-        int rc = sc == 1 ? gf::run<1>(a, (cudaStream_t)stream) : gf::run<3>(a, (cudaStream_t)stream);
-        if (rc != RF_OK) return rc;
+        // generic kernels: every iteration is a full filter; intermediate images alternate between a scratch
+        // image at the end of the workspace and dst, arranged so that the last one lands in dst
+        uint8_t *tmp = (uint8_t *)ws + gf::per_image_ws(sc, h, w) * (size_t)nn;
+        const uint8_t *in = src + i0 * img_px * sc;
+        for (int it = 0; it < iterations; ++it) {
+            uint8_t *out = ((iterations - 1 - it) & 1) ? tmp : dst + i0 * img_px * sc;
+            gf::Args a;
+            a.n = nn;
+            a.guide = guide + i0 * img_px * 3;
+            a.src = in;
+            a.dst = out;
+            a.ab = (float4 *)ws;
+            a.h = h;
+            a.w = w;
+            a.r = radius;
+            a.eps = (float)eps;
+            a.scale = 1.0 / ((double)k * k);
+            a.twa = 0;
+            a.seg_rows = 0;
+            int rc = sc == 1 ? gf::run<1>(a, (cudaStream_t)stream) : gf::run<3>(a, (cudaStream_t)stream);
+            if (rc != RF_OK) return rc;
+            in = out;
+        }
     }
     return RF_OK;
+}
+
+extern "C" int rf_guided_max_radius(void) { return gf::MAX_RADIUS; }
+
+extern "C" size_t rf_guided_workspace_bytes(int sc, int n, int h, int w, int radius)
+{
+    return workspace_bytes(sc, n, h, w, radius, 1);
+}
+
+extern "C" int rf_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst, int n, int h,
+                            int w, int radius, double eps, void *ws, size_t ws_bytes, void *stream)
+{
+    return guided_impl("rf_guided_u8", guide, gc, src, sc, dst, n, h, w, radius, eps, 1, ws, ws_bytes, stream);
+}
+
+extern "C" size_t rf_guided_iterated_workspace_bytes(int sc, int n, int h, int w, int radius, int iterations)
+{
+    return workspace_bytes(sc, n, h, w, radius, iterations);
+}
+
+extern "C" int rf_guided_iterated_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst, int n,
+                                     int h, int w, int radius, double eps, int iterations, void *ws, size_t ws_bytes,
+                                     void *stream)
+{
+    return guided_impl("rf_guided_iterated_u8", guide, gc, src, sc, dst, n, h, w, radius, eps, iterations, ws, ws_bytes,
+                       stream);
 }

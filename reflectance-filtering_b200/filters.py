@@ -81,10 +81,13 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 def guided_device(guide: torch.Tensor, src: torch.Tensor, radius: int, eps: float,
                   out: torch.Tensor | None = None,
-                  workspace: torch.Tensor | None = None) -> torch.Tensor:
+                  workspace: torch.Tensor | None = None, iterations: int = 1) -> torch.Tensor:
     """``cv2.ximgproc.guidedFilter(guide, src, radius, eps)`` for a batch (uint8 out, like src).
     A 1-channel ``src`` is filtered once; that equals every channel of filtering its 3-channel
-    replication."""
+    replication.  ``iterations`` > 1 applies the same guide again to the uint8 result (the guide statistics
+    are computed once, like a reused ``createGuidedFilter`` object); byte-identical to repeated calls."""
+    if iterations < 1:
+        raise ValueError("iterations must be >= 1")
     n, h, w, sc = _nhwc(src, "src")
     ng, hg, wg, gc = _nhwc(guide, "guide")
     if (ng, hg, wg) != (n, h, w):
@@ -95,11 +98,18 @@ def guided_device(guide: torch.Tensor, src: torch.Tensor, radius: int, eps: floa
     L = _native.lib()
     with torch.cuda.device(src.device):
         dev.bind_device(src.device)
-        need = int(L.rf_guided_workspace_bytes(sc, n, h, w, int(radius)))
-        ws = workspace if workspace is not None else _workspace(src.device, max(need, 16))
-        _native.check(L.rf_guided_u8(dev.ptr(guide), gc, dev.ptr(src), sc, dev.ptr(out), n, h, w,
-                                     int(radius), float(eps), dev.ptr(ws), ws.numel() * ws.element_size(),
-                                     dev.stream_ptr()))
+        if iterations == 1:
+            need = int(L.rf_guided_workspace_bytes(sc, n, h, w, int(radius)))
+            ws = workspace if workspace is not None else _workspace(src.device, max(need, 16))
+            _native.check(L.rf_guided_u8(dev.ptr(guide), gc, dev.ptr(src), sc, dev.ptr(out), n, h, w,
+                                         int(radius), float(eps), dev.ptr(ws), ws.numel() * ws.element_size(),
+                                         dev.stream_ptr()))
+        else:
+            need = int(L.rf_guided_iterated_workspace_bytes(sc, n, h, w, int(radius), int(iterations)))
+            ws = workspace if workspace is not None else _workspace(src.device, max(need, 16))
+            _native.check(L.rf_guided_iterated_u8(dev.ptr(guide), gc, dev.ptr(src), sc, dev.ptr(out), n, h, w,
+                                                  int(radius), float(eps), int(iterations), dev.ptr(ws),
+                                                  ws.numel() * ws.element_size(), dev.stream_ptr()))
     return out
 
 

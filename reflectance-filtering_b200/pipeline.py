@@ -61,12 +61,7 @@ class Pipeline(object):
         if iterations < 1:
             raise ValueError("iterations must be >= 1")
         cur = self.reflectance_u8(images)
-        radius, eps = int(sigma_spatial), sigma_color
-        spare = None
-        for _ in range(iterations):
-            res = filters.guided_device(guides, cur, radius, eps, out=spare)
-            spare, cur = cur, res
-        return cur
+        return filters.guided_device(guides, cur, int(sigma_spatial), sigma_color, iterations=iterations)
 
     # ---- host buffers in, host buffers out ----------------------------------------------------
     def run_host(self, kind: str, images: torch.Tensor, out: torch.Tensor,

@@ -198,6 +198,33 @@ def test_gf_ignores_workspace_contents(h, w, r, sc):
         assert mx <= 1 and frac < 2e-3, (fill, mx, frac)
 
 
+def test_gf_iterated_equals_repeated_calls():
+    """rf_guided_iterated_u8 (guide statistics cached, output fed back through the packed planes) must be
+    byte-identical to calling rf_guided_u8 on its own output -- fast path, generic path, gray and colour."""
+    for (h, w, r, sc, iters) in [(96, 120, 45, 1, 3), (72, 90, 7, 3, 2), (64, 64, 52, 1, 4), (40, 30, 45, 1, 3),
+                                 (50, 70, 70, 3, 3), (130, 700, 20, 1, 3)]:
+        n = 3
+        gd = np.stack([synth.flat(h, w, 700 + i) for i in range(n)])
+        src = np.stack([synth.natural(h, w, 800 + i) for i in range(n)])
+        src = src if sc == 3 else np.ascontiguousarray(src[..., 0])
+        dg, ds = dev_u8(gd), dev_u8(src)
+        want = ds
+        for _ in range(iters):
+            want = filters.guided_device(dg, want, r, 3.0)
+        got = filters.guided_device(dg, ds, r, 3.0, iterations=iters)
+        assert torch.equal(got, want), (h, w, r, sc, iters, lsb_stats(got.cpu().numpy(), want.cpu().numpy()))
+        # and against the oracle applied repeatedly (first image)
+        ref = src[0] if sc == 3 else np.repeat(src[0][..., None], 3, axis=2)
+        for _ in range(iters):
+            ref = oracle.guided(gd[0], ref, r, 3.0)
+        g0 = got[0].cpu().numpy()
+        g0 = g0 if sc == 3 else np.repeat(g0[..., None], 3, axis=2)
+        mx, frac = lsb_stats(g0, ref)
+        assert mx <= 1 and frac < 5e-3, (mx, frac)
+    with pytest.raises(ValueError):
+        filters.guided_device(dg, ds, r, 3.0, iterations=0)
+
+
 def test_gf_full_size_three_iterations_and_properties(net):
     # BASELINE config 3 on one image: CNN reflectance, 'flat' guide, c3 s45, 3 iterations with uint8
     # re-quantisation between them

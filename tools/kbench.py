@@ -55,6 +55,10 @@ def bench_gf():
             print(json.dumps({"kernel": "gf r=45 " + name, "shape": [n, h, w], "ms": med, "ms_min": mn,
                               "GB/s": px * bpp / (med * 1e-3) / 1e9, "frac_hbm": px * bpp / (med * 1e-3) / 1e9 / PEAK_HBM,
                               "Mpx/s": px / (med * 1e-3) / 1e6}))
+            med3, mn3 = timeit(lambda: filters.guided_device(guide, src, 45, 3.0, out=out, iterations=3))
+            print(json.dumps({"kernel": "gf r=45 " + name + " x3 (guide statistics cached)", "shape": [n, h, w],
+                              "ms": med3, "ms_min": mn3, "ms_per_iteration": med3 / 3,
+                              "frac_hbm": px * bpp * 3 / (med3 * 1e-3) / 1e9 / PEAK_HBM}))
 
 
 def bench_bf():
