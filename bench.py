@@ -65,19 +65,64 @@ def measured_peaks():
 # clock sampling during the timed region
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed region: an NVML polling thread
+    (every 10 ms, so even a 100 ms region gets samples), or a `nvidia-smi -lms` child if NVML is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.idx = gpu_index
+    def __init__(self, device):
+        self.device = device
         self.proc = None
         self.lines = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.handle = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(device).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                idx = device.index if hasattr(device, "index") else int(device)
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        except Exception:
+            self.handle = None
+
+    def sample_now(self):
+        if self.handle is None:
+            return
+        nv = self.nv
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            for name, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                              ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                              ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                              ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self._stop.is_set():
+            self.sample_now()
+            self._stop.wait(0.01)
 
     def start(self):
+        if self.handle is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
+            idx = self.device.index if hasattr(self.device, "index") else int(self.device)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                ["nvidia-smi", "-i", str(idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -89,6 +134,12 @@ class ClockSampler(object):
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.handle is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                    "sm_max_mhz": max(self.mx) if self.mx else None, "samples": len(self.sm),
+                    "reasons": sorted(self.reasons), "source": "nvml, 10 ms polling during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -112,7 +163,7 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -226,7 +277,7 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     # ---- device-resident timing -------------------------------------------------------------------
     for i in range(args.warmup):
         step(i)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(device)
     barrier()
     sampler.start()
     launches0 = _native.launch_count()
@@ -235,6 +286,7 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     for i in range(args.steps):
         step(args.warmup + i)
     e1.record()
+    sampler.sample_now()  # kernels of the timed region are still in flight here
     barrier()
     launches = _native.launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
