@@ -282,15 +282,18 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     sampler.start()
     launches0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i)
+        marks[i].record()  # per-step marks for best / median; the headline uses e0..e1 over all K steps
     e1.record()
     sampler.sample_now()  # kernels of the timed region are still in flight here
     barrier()
     launches = _native.launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
+    per_step = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(args.steps)]
     px_step = B * H * W
     value = world * px_step * args.steps / (ms_total * 1e-3) / 1e6
 
@@ -329,6 +332,23 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     barrier()
     cnn_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bf_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+
+    # ---- configs[0] shape: 3-channel BF with a copy of the image as joint (the colour kernel) ---------
+    bfc_ms = None
+    if not args.no_gf:
+        c_steps = max(3, args.steps // 4)
+        jcopy = dev_pool[0].clone()
+        cout = torch.empty_like(jcopy)
+        filters.joint_bilateral_device(jcopy, dev_pool[0], SIGMA_COLOR, SIGMA_SPATIAL, out=cout)
+        cev = [torch.cuda.Event(enable_timing=True) for _ in range(c_steps + 1)]
+        barrier()
+        cev[0].record()
+        for i in range(c_steps):
+            filters.joint_bilateral_device(jcopy, dev_pool[0], SIGMA_COLOR, SIGMA_SPATIAL, out=cout)
+            cev[i + 1].record()
+        barrier()
+        bfc_ms = float(np.mean([cev[i].elapsed_time(cev[i + 1]) for i in range(c_steps)]))
+        del jcopy, cout
 
     # ---- configs[2]: CNN -> GF(CNN, flat) c3 s45 x3, batch of 64 (secondary line, same JSON) ----------
     gf = None
@@ -431,6 +451,16 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         "roofline_cnn": cnn_roof,
         "cpu_baseline": cpu,
     }
+    line["step_ms"] = {"best": float(np.min(per_step)), "median": float(np.median(per_step)),
+                       "note": "per-step CUDA-event marks on rank 0 inside the timed region"}
+    if bfc_ms is not None:
+        ctaps = float(px_step) * taps / (bfc_ms * 1e-3)
+        line["roofline_bf_color"] = {
+            "kernel": "bf_color_kernel (configs[0] shape: 3-channel joint = copy of the 3-channel source), batch %d" % B,
+            "bound": "fp32", "launch_ms": bfc_ms, "achieved": ctaps * 10 / 1e9, "peak": alu_peak / 1e9,
+            "unit": "G FP32 lane-ops/s (SURVEY 8d: 10 lane-ops + 1 exp per tap)", "frac": ctaps * 10 / alu_peak,
+            "sfu": {"achieved_Gtap_s": ctaps / 1e9, "peak_Gtap_s": sfu_peak / 1e9, "frac": ctaps / sfu_peak},
+            "traffic": None}
     if gf is not None:
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         gpx = gf["batch"] * H * W
