@@ -245,6 +245,66 @@ def test_gf_full_size_three_iterations_and_properties(net):
     assert all(np.array_equal(o3[:, :, c], o1) for c in range(3))
 
 
+# ---- BASELINE configs 4 and 5 at full image size: oracle on crops ------------------------------------
+def _crop_regions(h, w, size):
+    """(y0, y1, x0, x1) of the four corners (image borders included), two edge strips and one interior block."""
+    m = size
+    return [(0, m, 0, m), (0, m, w - m, w), (h - m, h, 0, m), (h - m, h, w - m, w),
+            (h // 2, h // 2 + m, 0, m), (0, m, w // 3, w // 3 + m), (h // 2 - 7, h // 2 - 7 + m, w // 2 + 5, w // 2 + 5 + m)]
+
+
+def _check_on_crops(h, w, halo, size, run_oracle, got, max_frac):
+    """A filter output inside a region depends only on the input within `halo` of it: run the oracle on the
+    region grown by the halo (clipped at the image border, where the oracle's own border rule applies)."""
+    worst = (0, 0.0)
+    for (y0, y1, x0, x1) in _crop_regions(h, w, size):
+        ya, yb, xa, xb = max(0, y0 - halo), min(h, y1 + halo), max(0, x0 - halo), min(w, x1 + halo)
+        ref = run_oracle(ya, yb, xa, xb)[y0 - ya:y1 - ya, x0 - xa:x1 - xa]
+        mx, frac = lsb_stats(got[y0:y1, x0:x1], ref)
+        assert mx <= 1 and frac <= max_frac, ((y0, y1, x0, x1), mx, frac)
+        worst = max(worst, (mx, frac))
+    return worst
+
+
+def test_full_size_config5_4k_bf_and_gf_on_crops(net):
+    """3840x2160: CNN -> BF c15 s28 (r=42) and CNN -> GF c3 s45 (flat guide), checked against the oracle on
+    corner / edge / interior crops; plus batch-of-2 == single image (no cross-image state)."""
+    h, w = 2160, 3840
+    img = synth.natural(h, w, 5000)
+    gd = synth.flat(h, w, 5500)
+    d_img = dev_u8(img[None])
+    r8 = pipeline.Pipeline(net).reflectance_u8(d_img)
+    r8h = r8.cpu().numpy()[0]
+    r8h3 = np.repeat(r8h[:, :, None], 3, axis=2)
+    bf = filters.joint_bilateral_device(r8, r8, 15.0, 28.0, gray_replicated=True).cpu().numpy()[0]
+    _check_on_crops(h, w, 42, 64, lambda ya, yb, xa, xb: oracle.joint_bilateral(
+        r8h3[ya:yb, xa:xb].copy(), r8h3[ya:yb, xa:xb], -1, 15.0, 28.0)[:, :, 0], bf, 2e-3)
+    gf = filters.guided_device(dev_u8(gd[None]), r8, 45, 3.0).cpu().numpy()[0]
+    _check_on_crops(h, w, 90, 64, lambda ya, yb, xa, xb: oracle.guided(
+        gd[ya:yb, xa:xb], r8h3[ya:yb, xa:xb], 45, 3.0)[:, :, 0], gf, 5e-3)
+    flipped = r8.flip(1).contiguous()
+    two = torch.cat([r8, flipped])
+    bf2 = filters.joint_bilateral_device(two, two, 15.0, 28.0, gray_replicated=True)
+    assert torch.equal(bf2[0].cpu(), torch.from_numpy(bf))
+    assert torch.equal(bf2[1:], filters.joint_bilateral_device(flipped, flipped, 15.0, 28.0, gray_replicated=True))
+    # a vertical flip commutes with the filter up to the summation order of the taps: +-1 LSB on rounding ties
+    mx, frac = lsb_stats(bf2[1].flip(0).cpu().numpy(), bf)
+    assert mx <= 1 and frac < 1e-3, (mx, frac)
+
+
+def test_full_size_config4_1024x768_cnn_bf_on_crops(net, mlp):
+    """1024x768 (IIW scale): CNN (whole image vs the FP32 oracle) -> trunc -> BF(CNN,CNN) c20 s22 on crops."""
+    h, w = 768, 1024
+    img = synth.natural(h, w, 4000)
+    pipe = pipeline.Pipeline(net)
+    f32, r8 = net.forward_device(dev_u8(img[None]), want_f32=True, want_u8=True)
+    assert np.abs(f32.cpu().numpy()[0] - oracle.mlp_forward(mlp, img)).max() < CNN_TIGHT
+    out = pipe.cnn_bf(dev_u8(img[None]), 20.0, 22.0).cpu().numpy()[0]
+    r8h3 = np.repeat(r8.cpu().numpy()[0][:, :, None], 3, axis=2)
+    _check_on_crops(h, w, 33, 96, lambda ya, yb, xa, xb: oracle.joint_bilateral(
+        r8h3[ya:yb, xa:xb].copy(), r8h3[ya:yb, xa:xb], -1, 20.0, 22.0)[:, :, 0], out, 2e-3)
+
+
 # ---- pipeline, CLI, sharding ---------------------------------------------------------------------
 def test_pipeline_cnn_bf_config2(net, mlp):
     img = synth.natural(384, 512, 2000)
