@@ -45,6 +45,15 @@ __global__ void probe(uint32_t *out, uint32_t seed, float fs)
             if (KIND == 15) { float t; asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(t) : "r"(a[i])); a[i] = __float_as_uint(t) >> 3; }  // I2FP.F32.U32 (+SHF)
             if (KIND == 16) a[i] = __shfl_up_sync(0xffffffffu, a[i], 1) + 1;   // SHFL (+IADD)
             if (KIND == 17) { sm[(threadIdx.x + it) & 1023] = f[i]; f[i] += c1; }    // STS.32 (+FADD)
+            if (KIND == 18) asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(a[(i + 1) % ILP]), "r"(seed));  // IDP.4A
+            if (KIND == 19) a[i] = __funnelshift_r(a[i], seed, 24) + 1;                        // SHF (+IADD)
+            if (KIND == 20) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pc));   // FADD2
+            if (KIND == 21) { a[i] = a[i] * seed + 12345u; f[i] = fmaf(f[i], c0, c1); }        // IMAD + FFMA
+            if (KIND == 22) { asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(a[(i + 1) % ILP]), "r"(seed)); f[i] = fmaf(f[i], c0, c1); }  // IDP.4A + FFMA
+            if (KIND == 23) { a[i] = __float_as_uint(sm[a[i] & 255]) + it; }                 // LDS.32, 256-entry table, chained random index
+            if (KIND == 24) { a[i] = __float_as_uint(sm[(a[i] & 0) + (it & 255)]) + a[i]; }   // LDS.32 broadcast (all lanes one address)
+            if (KIND == 25) { a[i] = __float_as_uint(sm[((threadIdx.x & 31) + it + i) & 255]) + a[i]; }  // LDS.32 consecutive lanes
+            if (KIND == 26) { a[i] = __float_as_uint(sm[((threadIdx.x & 31) / 4 + it + i) & 255]) + a[i]; }  // LDS.32 4 lanes per address, 8 addresses
             if (KIND == 10) { float4 v = *reinterpret_cast<float4 *>(&sm[((threadIdx.x * 4) + (it & 7) * 128) & 1020]); f[i] += v.x + v.w; } // LDS.128 + 2 FADD
         }
     }
@@ -108,5 +117,14 @@ int main()
     run<15>("I2FP.F32.U32 (+SHF)", sms, 1);
     run<16>("SHFL.UP (+IADD)", sms, 1);
     run<17>("STS.32 (+FADD)", sms, 1);
+    run<23>("LDS.32 LUT256 random (+IADD,LOP)", sms, 1);
+    run<24>("LDS.32 broadcast (+IADD)", sms, 1);
+    run<25>("LDS.32 consecutive (+IADD)", sms, 1);
+    run<26>("LDS.32 8 addr x 4 lanes (+IADD)", sms, 1);
+    run<18>("IDP.4A", sms, 1);
+    run<19>("SHF (+IADD)", sms, 2);
+    run<20>("FADD2 (add.f32x2)", sms, 1);
+    run<21>("IMAD + FFMA", sms, 2);
+    run<22>("IDP.4A + FFMA", sms, 2);
     return 0;
 }
