@@ -110,6 +110,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// packed two-lane FP32 add on a 64-bit register pair (sm_100 FADD2)
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// -(x truncated to TF32): one LOP3 ((x & mask) ^ sign)
+__device__ __forceinline__ float neg_tf32_hi(float x)
+{
+    return __uint_as_float((__float_as_uint(x) & 0xFFFFE000u) ^ 0x80000000u);
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // shared memory map (bytes)
 struct Smem {
     int a_hi, a_lo, b, w0, bias, fw, lut, bar, slot, total;
@@ -187,11 +213,16 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *slot;
+    // warp-uniform copies (broadcast from lane 0) so that the MMA issue path stays on the uniform datapath
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot, 0);
+    const int wg_u = __shfl_sync(0xffffffffu, tid >> 7, 0);
+    const bool issuer_warp = __shfl_sync(0xffffffffu, warp & 3, 0) == 0;
     // 128 columns per warpgroup: D = [0,32), A_hi = [32,64), A_lo = [64,96)
-    const uint32_t tmem = tmem_base + wg * 128;
+    const uint32_t tmem = tmem_base + wg_u * 128;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // a warp may only touch its own 32 lanes
-    const uint32_t b_s = smem_u32(Bw), bar_s = smem_u32(bar);
+    const uint32_t b_s = smem_u32(Bw), bar_s = smem_u32(reinterpret_cast<uint64_t *>(smem + sm.bar) + wg_u);
+    // shared-memory matrix descriptor of a weight plane at byte address a: LBO 512, SBO 128, version 1
+    const uint64_t desc_base = make_desc(0, 512, 128);
     const float fb = fw[n_hidden * CW];
 
     uint32_t parity = 0;
@@ -203,7 +234,8 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
         const float x0 = lut[px[2]], x1 = lut[px[1]], x2 = lut[px[0]];  // BGR -> RGB, sRGB -> linear
 
         float h[CW];
-        float z = 0.0f;
+        // the fusing dot product runs as two interleaved partial sums (even / odd channels) in one 64-bit pair
+        unsigned long long z2 = pack2(0.0f, 0.0f);
         // conv0 + ReLU on the CUDA cores (Caffe order: dot, + bias, ReLU)
 #pragma unroll
         for (int o = 0; o < CW; o += 4) {
@@ -216,37 +248,45 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
                 s = fmaf(w.y, x1, s);
                 s = fmaf(w.z, x2, s);
                 h[o + u] = fmaxf(s + w.w, 0.0f);
-                z = fmaf(fv[u], h[o + u], z);
             }
+            ffma2(z2, pack2(fv[0], fv[1]), pack2(h[o], h[o + 1]));
+            ffma2(z2, pack2(fv[2], fv[3]), pack2(h[o + 2], h[o + 3]));
         }
         for (int l = 1; l < n_hidden; ++l) {
             // activations -> tensor memory: A_hi = the word itself (the tensor core truncates it to TF32),
-            // A_lo = what that truncation drops
+            // A_lo = what that truncation drops (packed: h + (-(h & mask)) on both halves of a register pair)
             {
                 float lo[CW];
 #pragma unroll
-                for (int o = 0; o < CW; ++o) lo[o] = tf32_lo(h[o]);
+                for (int o = 0; o < CW; o += 2) {
+                    const unsigned long long l2 =
+                        fadd2(pack2(h[o], h[o + 1]), pack2(neg_tf32_hi(h[o]), neg_tf32_hi(h[o + 1])));
+                    unpack2(l2, lo[o], lo[o + 1]);
+                }
                 tmem_store32(tmem + 32 + lane_sel, h);
                 tmem_store32(tmem + 64 + lane_sel, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");  // this warpgroup only
-            if (wtid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t bh = b_s + (l - 1) * 2 * B_BYTES, bl = bh + B_BYTES;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg_u) : "memory");  // this warpgroup only
+            if (issuer_warp) {
+                if (elect_one()) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t bh = b_s + (l - 1) * 2 * B_BYTES, bl = bh + B_BYTES;
+                    const uint64_t dh = desc_base | (uint64_t)((bh >> 4) & 0x3FFF);
+                    const uint64_t dl = desc_base | (uint64_t)((bl >> 4) & 0x3FFF);
 #pragma unroll
-                for (int combo = 0; combo < 3; ++combo) {
-                    const uint32_t at = tmem + (combo == 2 ? 64 : 32);
-                    const uint32_t bs = combo == 1 ? bl : bh;
+                    for (int combo = 0; combo < 3; ++combo) {
+                        const uint32_t at = tmem + (combo == 2 ? 64 : 32);
+                        const uint64_t bd0 = combo == 1 ? dl : dh;
 #pragma unroll
-                    for (int j = 0; j < CW / 8; ++j) {
-                        const uint64_t bd = make_desc(bs + j * 2 * 512, 512, 128);
-                        mma_tf32_ts(tmem, at + 8 * j, bd, (combo | j) != 0);
+                        for (int j = 0; j < CW / 8; ++j)  // next K step: two core-matrix columns = 1024 B = 64 units
+                            mma_tf32_ts(tmem, at + 8 * j, bd0 + (uint64_t)(j * 64), (combo | j) != 0);
                     }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_s)
+                                 : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_s)
-                             : "memory");
+                __syncwarp();
             }
             mbar_wait(bar_s, parity);
             parity ^= 1;
@@ -265,21 +305,26 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // + bias (packed add), ReLU, fuse FMA (packed): Caffe order dot, + bias, ReLU
             const float4 *bl_ = reinterpret_cast<const float4 *>(bias + l * CW);
             const float4 *fl = reinterpret_cast<const float4 *>(fw + l * CW);
 #pragma unroll
             for (int o = 0; o < CW; o += 4) {
                 const float4 b4 = bl_[o >> 2], f4 = fl[o >> 2];
-                h[o] = fmaxf(__uint_as_float(acc[o]) + b4.x, 0.0f);
-                h[o + 1] = fmaxf(__uint_as_float(acc[o + 1]) + b4.y, 0.0f);
-                h[o + 2] = fmaxf(__uint_as_float(acc[o + 2]) + b4.z, 0.0f);
-                h[o + 3] = fmaxf(__uint_as_float(acc[o + 3]) + b4.w, 0.0f);
-                z = fmaf(f4.x, h[o], z);
-                z = fmaf(f4.y, h[o + 1], z);
-                z = fmaf(f4.z, h[o + 2], z);
-                z = fmaf(f4.w, h[o + 3], z);
+                float t0, t1, t2, t3;
+                unpack2(fadd2(pack2(__uint_as_float(acc[o]), __uint_as_float(acc[o + 1])), pack2(b4.x, b4.y)), t0, t1);
+                unpack2(fadd2(pack2(__uint_as_float(acc[o + 2]), __uint_as_float(acc[o + 3])), pack2(b4.z, b4.w)), t2, t3);
+                h[o] = fmaxf(t0, 0.0f);
+                h[o + 1] = fmaxf(t1, 0.0f);
+                h[o + 2] = fmaxf(t2, 0.0f);
+                h[o + 3] = fmaxf(t3, 0.0f);
+                ffma2(z2, pack2(f4.x, f4.y), pack2(h[o], h[o + 1]));
+                ffma2(z2, pack2(f4.z, f4.w), pack2(h[o + 2], h[o + 3]));
             }
         }
+        float z_even, z_odd;
+        unpack2(z2, z_even, z_odd);
+        const float z = z_even + z_odd;
         const float r = __fdiv_rn(1.0f, 1.0f + expf(-(z + fb)));
         if (valid) {
             if (out_f32) out_f32[p] = r;
