@@ -32,7 +32,6 @@ constexpr int TILE_M = 128;
 constexpr int CW = 32;  // hidden width
 constexpr int WGS = 2;            // warpgroups per CTA, each runs its own tile pipeline
 constexpr int THREADS = 128 * WGS;
-constexpr int B_BYTES = CW * CW * 4;      // 4 KB per weight plane
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -136,25 +135,47 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+// this thread's TMEM lane, 8 consecutive columns
+__device__ __forceinline__ void tmem_store8(uint32_t taddr, float v0, float v1, float v2, float v3, float v4, float v5,
+                                            float v6, float v7)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v0),
+                 "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6), "f"(v7)
+                 : "memory");
+}
+
+constexpr int K0 = 8;                     // conv0 as an MMA: K = (r, g, b, 1, 0, 0, 0, 0), the 1 carries the bias
+constexpr int KH = 40;                    // hidden layers: 32 activations, the constant 1 (bias row), 7 x padding
+constexpr int B0_BYTES = CW * K0 * 4;     // 1 KB per conv0 weight plane
+constexpr int BH_BYTES = CW * KH * 4;     // 5 KB per hidden weight plane
+
+// tensor-memory columns of one warpgroup pipeline (128 allocated)
+constexpr int T_D = 0;       // [0, 32)    accumulator
+constexpr int T_AH = 32;     // [32, 72)   A_hi: activations (the tensor core truncates them to TF32) + (1, 0 x 7)
+constexpr int T_AL = 72;     // [72, 104)  A_lo: what the truncation drops
+constexpr int T_XH = 104;    // [104, 112) conv0 A_hi: (r, g, b, 1, 0 x 4) linear RGB
+constexpr int T_XL = 112;    // [112, 120) conv0 A_lo
+
 // shared memory map (bytes)
 struct Smem {
-    int a_hi, a_lo, b, w0, bias, fw, lut, bar, slot, total;
+    int b0, b, fw, lut_hi, lut_lo, bar, slot, total;
 };
 __host__ __device__ inline Smem smem_map(int n_hidden)
 {
     Smem s;
-    s.a_hi = 0;                                        // (activations live in tensor memory)
-    s.a_lo = 0;
-    s.b = 0;                                           // per MMA layer: hi plane, lo plane (shared by the warpgroups)
-    s.w0 = s.b + (n_hidden - 1) * 2 * B_BYTES;         // 32 x 3 floats (padded to 128)
-    s.bias = s.w0 + 128 * 4;                           // n_hidden x 32
-    s.fw = s.bias + n_hidden * CW * 4;                 // n_hidden x 32, then fuse bias
-    s.lut = s.fw + (n_hidden * CW + 4) * 4;            // 256
-    s.bar = s.lut + 256 * 4;                           // one 8-byte mbarrier per warpgroup
+    s.b0 = 0;                                          // conv0: hi plane, lo plane
+    s.b = s.b0 + 2 * B0_BYTES;                         // per hidden MMA layer: hi plane, lo plane
+    s.fw = s.b + (n_hidden - 1) * 2 * BH_BYTES;        // fusing weights n_hidden x 32, then the fuse bias
+    s.lut_hi = s.fw + (n_hidden * CW + 4) * 4;         // sRGB -> linear table and its TF32 remainder
+    s.lut_lo = s.lut_hi + 256 * 4;
+    s.bar = s.lut_lo + 256 * 4;                        // one 8-byte mbarrier per warpgroup
     s.slot = s.bar + 8 * WGS;
     s.total = s.slot + 8;
     return s;
 }
+
+// byte offset of element (n, k) in a canonical K-major no-swizzle plane with 32 rows (N)
+__device__ __forceinline__ int plane_off(int n, int k) { return (k >> 2) * 512 + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4; }
 
 __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict__ params, int n_hidden,
                                                          const float *__restrict__ lut_g,
@@ -164,40 +185,37 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
     extern __shared__ __align__(1024) uint8_t smem[];
     const Smem sm = smem_map(n_hidden);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, wtid = tid & 127;
-    float *Bw = reinterpret_cast<float *>(smem + sm.b);
-    float *W0 = reinterpret_cast<float *>(smem + sm.w0);
-    float *bias = reinterpret_cast<float *>(smem + sm.bias);
     float *fw = reinterpret_cast<float *>(smem + sm.fw);
-    float *lut = reinterpret_cast<float *>(smem + sm.lut);
+    float *lut_hi = reinterpret_cast<float *>(smem + sm.lut_hi);
+    float *lut_lo = reinterpret_cast<float *>(smem + sm.lut_lo);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + sm.bar) + wg;
     uint32_t *slot = reinterpret_cast<uint32_t *>(smem + sm.slot);
 
     // ---- stage the model: parameter block is [W0 | b0 | W1 | b1 | ... | fuse_w | fuse_b] ----------------
-    // conv0 as 32 x float4 (w_r, w_g, w_b, bias): one LDS.128 per output channel
-    for (int i = tid; i < CW; i += THREADS) {
-        W0[4 * i] = params[3 * i];
-        W0[4 * i + 1] = params[3 * i + 1];
-        W0[4 * i + 2] = params[3 * i + 2];
-        W0[4 * i + 3] = params[96 + i];
+    // Every layer becomes a pair of K-major planes W[n][k] (the word itself: the tensor core reads its TF32
+    // truncation; and the remainder), with the bias as the extra row k = 3 (conv0) / k = 32 (hidden).
+    for (int i = tid; i < CW * K0; i += THREADS) {
+        const int n = i / K0, k = i % K0;
+        const float wv = k < 3 ? params[3 * n + k] : (k == 3 ? params[96 + n] : 0.0f);
+        *reinterpret_cast<float *>(smem + sm.b0 + plane_off(n, k)) = wv;
+        *reinterpret_cast<float *>(smem + sm.b0 + B0_BYTES + plane_off(n, k)) = tf32_lo(wv);
     }
-    for (int i = tid; i < 256; i += THREADS) lut[i] = lut_g[i];
+    for (int i = tid; i < 256; i += THREADS) {
+        const float v = lut_g[i];
+        lut_hi[i] = v;
+        lut_lo[i] = tf32_lo(v);
+    }
     {
-        const float *q = params + 96;
-        for (int l = 0; l < n_hidden; ++l) {
-            if (l > 0) {
-                // W_l[n][k] -> canonical K-major planes: off(n,k) = (k/4)*512 + (n/8)*128 + (n%8)*16 + (k%4)*4
-                float *hi = Bw + (l - 1) * (2 * B_BYTES / 4), *lo = hi + B_BYTES / 4;
-                for (int i = tid; i < CW * CW; i += THREADS) {
-                    const int n = i / CW, k = i % CW;
-                    const int off = ((k >> 2) * 512 + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4) >> 2;
-                    const float wv = q[i];
-                    hi[off] = wv;  // the tensor core reads the TF32 truncation of this word
-                    lo[off] = tf32_lo(wv);
-                }
-                q += CW * CW;
+        const float *q = params + 96 + CW;
+        for (int l = 1; l < n_hidden; ++l) {
+            uint8_t *hi = smem + sm.b + (l - 1) * 2 * BH_BYTES, *lo = hi + BH_BYTES;
+            for (int i = tid; i < CW * KH; i += THREADS) {
+                const int n = i / KH, k = i % KH;
+                const float wv = k < CW ? q[n * CW + k] : (k == CW ? q[CW * CW + n] : 0.0f);
+                *reinterpret_cast<float *>(hi + plane_off(n, k)) = wv;
+                *reinterpret_cast<float *>(lo + plane_off(n, k)) = tf32_lo(wv);
             }
-            for (int i = tid; i < CW; i += THREADS) bias[l * CW + i] = q[i];
-            q += CW;
+            q += CW * CW + CW;
         }
         for (int i = tid; i < n_hidden * CW + 1; i += THREADS) fw[i] = q[i];
     }
@@ -217,71 +235,67 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot, 0);
     const int wg_u = __shfl_sync(0xffffffffu, tid >> 7, 0);
     const bool issuer_warp = __shfl_sync(0xffffffffu, warp & 3, 0) == 0;
-    // 128 columns per warpgroup: D = [0,32), A_hi = [32,64), A_lo = [64,96)
     const uint32_t tmem = tmem_base + wg_u * 128;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // a warp may only touch its own 32 lanes
-    const uint32_t b_s = smem_u32(Bw), bar_s = smem_u32(reinterpret_cast<uint64_t *>(smem + sm.bar) + wg_u);
-    // shared-memory matrix descriptor of a weight plane at byte address a: LBO 512, SBO 128, version 1
+    const uint32_t bar_s = smem_u32(reinterpret_cast<uint64_t *>(smem + sm.bar) + wg_u);
+    // shared-memory matrix descriptors: LBO 512 (next 4 k), SBO 128 (next 8 n), version 1; + (address >> 4)
     const uint64_t desc_base = make_desc(0, 512, 128);
+    const uint32_t b0_s = smem_u32(smem + sm.b0), b_s = smem_u32(smem + sm.b);
     const float fb = fw[n_hidden * CW];
+    // the constant 1 (bias row) and the padding of the hidden A_hi block: written once, never overwritten
+    tmem_store8(tmem + T_AH + CW + lane_sel, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
 
     uint32_t parity = 0;
     const size_t n_tiles = (n_px + TILE_M - 1) / TILE_M;
-    for (size_t tile = (size_t)blockIdx.x * WGS + wg; tile < n_tiles; tile += (size_t)gridDim.x * WGS) {
+    const size_t tile0 = (size_t)blockIdx.x * WGS + wg, tile_step = (size_t)gridDim.x * WGS;
+    auto load_px = [&](size_t tile, uint32_t &c0, uint32_t &c1, uint32_t &c2) {
+        const size_t p = tile * TILE_M + wtid;
+        const uint8_t *px = bgr + 3 * (p < n_px ? p : n_px - 1);
+        c0 = px[0];
+        c1 = px[1];
+        c2 = px[2];
+    };
+    uint32_t cb = 0, cg = 0, cr = 0;
+    if (tile0 < n_tiles) load_px(tile0, cb, cg, cr);
+    for (size_t tile = tile0; tile < n_tiles; tile += tile_step) {
         const size_t p = tile * TILE_M + wtid;
         const bool valid = p < n_px;
-        const uint8_t *px = bgr + 3 * (valid ? p : n_px - 1);
-        const float x0 = lut[px[2]], x1 = lut[px[1]], x2 = lut[px[0]];  // BGR -> RGB, sRGB -> linear
+        // BGR -> RGB, sRGB -> linear (exact table), split for the tensor core
+        tmem_store8(tmem + T_XH + lane_sel, lut_hi[cr], lut_hi[cg], lut_hi[cb], 1.0f, 0.0f, 0.0f, 0.0f, 0.0f);
+        tmem_store8(tmem + T_XL + lane_sel, lut_lo[cr], lut_lo[cg], lut_lo[cb], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
+        // the next tile's pixel arrives while this one runs through the layers
+        if (tile + tile_step < n_tiles) load_px(tile + tile_step, cb, cg, cr);
 
-        float h[CW];
         // the fusing dot product runs as two interleaved partial sums (even / odd channels) in one 64-bit pair
         unsigned long long z2 = pack2(0.0f, 0.0f);
-        // conv0 + ReLU on the CUDA cores (Caffe order: dot, + bias, ReLU)
-#pragma unroll
-        for (int o = 0; o < CW; o += 4) {
-            const float4 f4 = *reinterpret_cast<const float4 *>(fw + o);
-            const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 w = *reinterpret_cast<const float4 *>(W0 + 4 * (o + u));
-                float s = w.x * x0;
-                s = fmaf(w.y, x1, s);
-                s = fmaf(w.z, x2, s);
-                h[o + u] = fmaxf(s + w.w, 0.0f);
-            }
-            ffma2(z2, pack2(fv[0], fv[1]), pack2(h[o], h[o + 1]));
-            ffma2(z2, pack2(fv[2], fv[3]), pack2(h[o + 2], h[o + 3]));
-        }
-        for (int l = 1; l < n_hidden; ++l) {
-            // activations -> tensor memory: A_hi = the word itself (the tensor core truncates it to TF32),
-            // A_lo = what that truncation drops (packed: h + (-(h & mask)) on both halves of a register pair)
-            {
-                float lo[CW];
-#pragma unroll
-                for (int o = 0; o < CW; o += 2) {
-                    const unsigned long long l2 =
-                        fadd2(pack2(h[o], h[o + 1]), pack2(neg_tf32_hi(h[o]), neg_tf32_hi(h[o + 1])));
-                    unpack2(l2, lo[o], lo[o + 1]);
-                }
-                tmem_store32(tmem + 32 + lane_sel, h);
-                tmem_store32(tmem + 64 + lane_sel, lo);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            }
+        for (int l = 0; l < n_hidden; ++l) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg_u) : "memory");  // this warpgroup only
             if (issuer_warp) {
                 if (elect_one()) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t bh = b_s + (l - 1) * 2 * B_BYTES, bl = bh + B_BYTES;
-                    const uint64_t dh = desc_base | (uint64_t)((bh >> 4) & 0x3FFF);
-                    const uint64_t dl = desc_base | (uint64_t)((bl >> 4) & 0x3FFF);
+                    if (l == 0) {
+                        // D = X_hi W0_hi + X_hi W0_lo + X_lo W0_hi   (K = 8: one instruction each)
+                        const uint64_t dh = desc_base | (uint64_t)((b0_s >> 4) & 0x3FFF);
+                        const uint64_t dl = desc_base | (uint64_t)(((b0_s + B0_BYTES) >> 4) & 0x3FFF);
+                        mma_tf32_ts(tmem + T_D, tmem + T_XH, dh, 0);
+                        mma_tf32_ts(tmem + T_D, tmem + T_XH, dl, 1);
+                        mma_tf32_ts(tmem + T_D, tmem + T_XL, dh, 1);
+                    } else {
+                        // D = A_hi W_hi + A_hi W_lo (K = 40: activations and the bias row) + A_lo W_hi (K = 32)
+                        const uint32_t bh = b_s + (l - 1) * 2 * BH_BYTES, bl = bh + BH_BYTES;
+                        const uint64_t dh = desc_base | (uint64_t)((bh >> 4) & 0x3FFF);
+                        const uint64_t dl = desc_base | (uint64_t)((bl >> 4) & 0x3FFF);
 #pragma unroll
-                    for (int combo = 0; combo < 3; ++combo) {
-                        const uint32_t at = tmem + (combo == 2 ? 64 : 32);
-                        const uint64_t bd0 = combo == 1 ? dl : dh;
+                        for (int j = 0; j < KH / 8; ++j)  // next K step: two core-matrix columns = 1024 B = 64 units
+                            mma_tf32_ts(tmem + T_D, tmem + T_AH + 8 * j, dh + (uint64_t)(j * 64), j != 0);
 #pragma unroll
-                        for (int j = 0; j < CW / 8; ++j)  // next K step: two core-matrix columns = 1024 B = 64 units
-                            mma_tf32_ts(tmem, at + 8 * j, bd0 + (uint64_t)(j * 64), (combo | j) != 0);
+                        for (int j = 0; j < KH / 8; ++j)
+                            mma_tf32_ts(tmem + T_D, tmem + T_AH + 8 * j, dl + (uint64_t)(j * 64), 1);
+#pragma unroll
+                        for (int j = 0; j < CW / 8; ++j)
+                            mma_tf32_ts(tmem + T_D, tmem + T_AL + 8 * j, dh + (uint64_t)(j * 64), 1);
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_s)
                                  : "memory");
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
             parity ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t acc[CW];
-            const uint32_t taddr = tmem + lane_sel;
+            const uint32_t taddr = tmem + T_D + lane_sel;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -305,21 +319,31 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // + bias (packed add), ReLU, fuse FMA (packed): Caffe order dot, + bias, ReLU
-            const float4 *bl_ = reinterpret_cast<const float4 *>(bias + l * CW);
+            // the accumulator already holds dot + bias (Caffe order); ReLU, fuse FMA (packed)
+            float h[CW];
             const float4 *fl = reinterpret_cast<const float4 *>(fw + l * CW);
 #pragma unroll
             for (int o = 0; o < CW; o += 4) {
-                const float4 b4 = bl_[o >> 2], f4 = fl[o >> 2];
-                float t0, t1, t2, t3;
-                unpack2(fadd2(pack2(__uint_as_float(acc[o]), __uint_as_float(acc[o + 1])), pack2(b4.x, b4.y)), t0, t1);
-                unpack2(fadd2(pack2(__uint_as_float(acc[o + 2]), __uint_as_float(acc[o + 3])), pack2(b4.z, b4.w)), t2, t3);
-                h[o] = fmaxf(t0, 0.0f);
-                h[o + 1] = fmaxf(t1, 0.0f);
-                h[o + 2] = fmaxf(t2, 0.0f);
-                h[o + 3] = fmaxf(t3, 0.0f);
+                const float4 f4 = fl[o >> 2];
+                h[o] = fmaxf(__uint_as_float(acc[o]), 0.0f);
+                h[o + 1] = fmaxf(__uint_as_float(acc[o + 1]), 0.0f);
+                h[o + 2] = fmaxf(__uint_as_float(acc[o + 2]), 0.0f);
+                h[o + 3] = fmaxf(__uint_as_float(acc[o + 3]), 0.0f);
                 ffma2(z2, pack2(f4.x, f4.y), pack2(h[o], h[o + 1]));
                 ffma2(z2, pack2(f4.z, f4.w), pack2(h[o + 2], h[o + 3]));
+            }
+            if (l + 1 < n_hidden) {
+                // activations -> tensor memory as the next layer's A: A_hi = the word itself, A_lo = what the
+                // TF32 truncation drops (packed: h + (-(h & mask)) on both halves of a register pair)
+                float lo[CW];
+#pragma unroll
+                for (int o = 0; o < CW; o += 2) {
+                    const unsigned long long l2 =
+                        fadd2(pack2(h[o], h[o + 1]), pack2(neg_tf32_hi(h[o]), neg_tf32_hi(h[o + 1])));
+                    unpack2(l2, lo[o], lo[o + 1]);
+                }
+                tmem_store32(tmem + T_AH + lane_sel, h);
+                tmem_store32(tmem + T_AL + lane_sel, lo);
             }
         }
         float z_even, z_odd;
