@@ -422,11 +422,13 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0  # dense TF32 = half the measured bf16 rate
     cnn_roof = {"kernel": "mlp_tc_kernel (tcgen05.mma kind::tf32, A from TMEM, 3x split operands)", "bound": "tensor",
                 "launch_ms": cnn_ms, "achieved": cnn_flops / (cnn_ms * 1e-3) / 1e12, "peak": tf32_peak,
-                "unit": "TFLOP/s (algorithmic 8,704 FLOP/px; the split issues 3x the MMAs of conv1-4)",
+                "unit": "TFLOP/s (algorithmic 8,704 FLOP/px; 3xTF32 split operands: 59 MMAs of 128x32x8 per 128-pixel tile, "
+                        "conv0 and all biases included)",
                 "frac": cnn_flops / (cnn_ms * 1e-3) / 1e12 / tf32_peak,
                 "vs_fp32_cuda_core_peak": cnn_flops / (cnn_ms * 1e-3) / (alu_peak * 2),
-                "note": "epilogue / latency bound by construction: K = N = 32 per layer, activations round-trip "
-                        "TMEM -> registers -> TMEM between layers (DESIGN.md K2)"}
+                "note": "latency bound by construction: K = N = 32 per layer, activations round-trip TMEM -> registers "
+                        "(ReLU, fuse dot, hi/lo split) -> TMEM between layers; four tile pipelines per SM (TMEM "
+                        "capacity) overlap each other (DESIGN.md K2)"}
 
     cpu = None
     if world == 1 and not args.no_cpu:

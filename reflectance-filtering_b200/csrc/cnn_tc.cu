@@ -30,7 +30,7 @@ namespace cnntc {
 
 constexpr int TILE_M = 128;
 constexpr int CW = 32;  // hidden width
-constexpr int WGS = 2;            // warpgroups per CTA, each runs its own tile pipeline
+constexpr int WGS = 5;            // warpgroups per CTA (one CTA per SM), each runs its own tile pipeline
 constexpr int THREADS = 128 * WGS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -149,12 +149,16 @@ constexpr int KH = 40;                    // hidden layers: 32 activations, the 
 constexpr int B0_BYTES = CW * K0 * 4;     // 1 KB per conv0 weight plane
 constexpr int BH_BYTES = CW * KH * 4;     // 5 KB per hidden weight plane
 
-// tensor-memory columns of one warpgroup pipeline (128 allocated)
+// Tensor-memory columns.  A layer's sync chain (st -> barrier -> MMA issue -> commit -> mbarrier -> ld) is latency
+// that only other pipelines can hide (measured: 2 pipelines per SM 0.97 ms, 4 pipelines 0.69 ms), and tensor
+// memory (512 columns) bounds their number: 96 columns per pipeline + ONE constant block shared by all.
 constexpr int T_D = 0;       // [0, 32)    accumulator
-constexpr int T_AH = 32;     // [32, 72)   A_hi: activations (the tensor core truncates them to TF32) + (1, 0 x 7)
-constexpr int T_AL = 72;     // [72, 104)  A_lo: what the truncation drops
-constexpr int T_XH = 104;    // [104, 112) conv0 A_hi: (r, g, b, 1, 0 x 4) linear RGB
-constexpr int T_XL = 112;    // [112, 120) conv0 A_lo
+constexpr int T_AH = 32;     // [32, 64)   A_hi: activations (the tensor core truncates them to TF32)
+constexpr int T_AL = 64;     // [64, 96)   A_lo: what the truncation drops
+constexpr int T_XH = 32;     // [32, 40)   conv0 A_hi: (r, g, b, 1, 0 x 4) linear RGB   (before the first activations land)
+constexpr int T_XL = 40;     // [40, 48)   conv0 A_lo
+constexpr int T_COLS = 96;
+constexpr int T_ONE = WGS * T_COLS;  // [480, 488) the K-step that carries the bias row: (1, 0 x 7) in every lane
 
 // shared memory map (bytes)
 struct Smem {
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // weight planes -> visible to the tensor core
@@ -235,15 +239,22 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot, 0);
     const int wg_u = __shfl_sync(0xffffffffu, tid >> 7, 0);
     const bool issuer_warp = __shfl_sync(0xffffffffu, warp & 3, 0) == 0;
-    const uint32_t tmem = tmem_base + wg_u * 128;
+    const uint32_t tmem = tmem_base + wg_u * T_COLS;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // a warp may only touch its own 32 lanes
     const uint32_t bar_s = smem_u32(reinterpret_cast<uint64_t *>(smem + sm.bar) + wg_u);
     // shared-memory matrix descriptors: LBO 512 (next 4 k), SBO 128 (next 8 n), version 1; + (address >> 4)
     const uint64_t desc_base = make_desc(0, 512, 128);
     const uint32_t b0_s = smem_u32(smem + sm.b0), b_s = smem_u32(smem + sm.b);
     const float fb = fw[n_hidden * CW];
-    // the constant 1 (bias row) and the padding of the hidden A_hi block: written once, never overwritten
-    tmem_store8(tmem + T_AH + CW + lane_sel, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
+    // the constant 1 (bias row) and its padding: written once by warpgroup 0 for all 128 lanes, read by every
+    // pipeline's MMAs
+    if (wg_u == 0) {
+        tmem_store8(tmem_base + T_ONE + lane_sel, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     uint32_t parity = 0;
     const size_t n_tiles = (n_px + TILE_M - 1) / TILE_M;
@@ -289,10 +300,12 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
                         const uint64_t dl = desc_base | (uint64_t)((bl >> 4) & 0x3FFF);
 #pragma unroll
                         for (int j = 0; j < KH / 8; ++j)  // next K step: two core-matrix columns = 1024 B = 64 units
-                            mma_tf32_ts(tmem + T_D, tmem + T_AH + 8 * j, dh + (uint64_t)(j * 64), j != 0);
+                            mma_tf32_ts(tmem + T_D, j < CW / 8 ? tmem + T_AH + 8 * j : tmem_base + T_ONE,
+                                        dh + (uint64_t)(j * 64), j != 0);
 #pragma unroll
                         for (int j = 0; j < KH / 8; ++j)
-                            mma_tf32_ts(tmem + T_D, tmem + T_AH + 8 * j, dl + (uint64_t)(j * 64), 1);
+                            mma_tf32_ts(tmem + T_D, j < CW / 8 ? tmem + T_AH + 8 * j : tmem_base + T_ONE,
+                                        dl + (uint64_t)(j * 64), 1);
 #pragma unroll
                         for (int j = 0; j < CW / 8; ++j)
                             mma_tf32_ts(tmem + T_D, tmem + T_AL + 8 * j, dh + (uint64_t)(j * 64), 1);
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(THREADS) mlp_tc_kernel(const float *__restrict
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 bool supported(int width, int n_hidden) { return width == CW && n_hidden >= 2 && n_hidden <= 8; }
@@ -385,10 +398,8 @@ int launch(const float *d_params, int n_hidden, const float *d_lut, const uint8_
     RF_CUDA_TRY(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
         RF_CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        // resident CTAs per SM are bounded by shared memory (the occupancy API under-reports kernels that
-        // use TMEM); registers allow 6, TMEM (32 of 512 columns per CTA) allows 16
-        int o = (int)((227 * 1024) / (smem + 1024));
-        occ[dev & 63] = o < 1 ? 1 : (o > 2 ? 2 : o);  // tensor memory: 256 of the SM's 512 columns per CTA
+        // one CTA per SM: it allocates all 512 tensor-memory columns for its WGS pipelines
+        occ[dev & 63] = 1;
         configured[dev & 63] = true;
     }
     const size_t n_tiles = (n_px + TILE_M - 1) / TILE_M;
