@@ -4,23 +4,30 @@
 // shipped graph family (uniform hidden width 32; network_definition.prototxt:17-165).  All convolutions
 // are 1x1, so each hidden layer is D[128 px x 32] = A[128 px x 32] * W^T[32 x 32] per tile of 128 pixels.
 //
-//   * conv0 (K = 3) and the 160 -> 1 fusing layer are poor MMA shapes: conv0 runs on the CUDA cores from
-//     the exact sRGB->linear table, the fusing layer is a running 32-FMA dot product in every epilogue;
-//   * conv1..conv4 run as tcgen05.mma kind::tf32 (M=128, N=32, K=8) with the accumulator in TMEM.  Single
-//     TF32 misses the 1e-3 tolerance (7e-3), so operands are split x = hi + lo with
+//   * every layer runs as tcgen05.mma kind::tf32 (M=128, N=32, K=8) with the accumulator in TMEM: conv0 as
+//     K = 8 over (r, g, b, 1, 0...) from the exact sRGB->linear table, conv1..conv4 as K = 40 = 32 activations +
+//     one K-step whose A block is the constant (1, 0 x 7) and whose weight row is the bias -- so the
+//     accumulator already holds Caffe's dot + bias.  Only the 160 -> 1 fusing layer stays on the CUDA cores,
+//     as a running packed (FFMA2) dot product in every epilogue;
+//   * single TF32 misses the 1e-3 tolerance (7e-3), so operands are split x = hi + lo with
 //     hi = x truncated to TF32 (what the tensor core reads anyway) and lo = x - hi, and each layer issues
-//     A_hi*W_hi + A_hi*W_lo + A_lo*W_hi (12 MMAs); measured max error vs the FP32 oracle: ~3e-6;
+//     A_hi*W_hi + A_hi*W_lo + A_lo*W_hi: 3 MMAs for conv0, 5 + 5 + 4 per hidden layer, 59 per tile; measured
+//     max error vs the FP32 oracle ~8e-6;
 //   * activations never leave the SM and never touch shared memory: epilogue = tcgen05.ld (thread t of
-//     warp w owns TMEM lane 32w+t = pixel t of the tile, all 32 outputs) -> +bias, ReLU, fuse FMA, split
-//     -> tcgen05.st back into tensor memory as the A operand of the next layer's MMAs (A-from-TMEM form);
-//     only the 32x32 weight planes are read from shared memory (canonical K-major no-swizzle UMMA
-//     layout).  A first version staged A in shared memory and was bound by its bandwidth (67 % of
-//     the LSU wavefront peak, profiles/r01_cnn_tc_ncu_full.txt);
-//   * persistent CTAs of two warpgroups, each warpgroup runs its own tile pipeline (own A planes, TMEM
-//     columns, mbarrier, named barrier) over weights staged once per CTA; 2 CTAs per SM = four pipelines
-//     overlapping each other's MMA / barrier latency.
-// SASS: UTCHMMA / LDTM / UTCBAR (tcgen05.mma / .ld / .commit).  The exact-FP32 kernel in cnn.cu remains
-// for other widths and as the in-library cross-check (RF_CNN_FP32=1).
+//     warp w owns TMEM lane 32w+t = pixel t of the tile, all 32 outputs) -> ReLU, fuse FFMA2, split (one LOP3 +
+//     half an FADD2 per value) -> tcgen05.st back into tensor memory as the A operand of the next layer's MMAs
+//     (A-from-TMEM form); only the weight planes are read from shared memory (canonical K-major no-swizzle
+//     UMMA layout);
+//   * the MMA issue path is warp-uniform (broadcast values + elect.sync): 14 back-to-back UTCHMMA per layer.
+//     A first version issued from `if (thread == 0)` and spent ~16 instructions of per-operand R2UR
+//     broadcasts per MMA while 127 threads waited (1.02 -> 0.76 ms);
+//   * what bounds it: the per-layer sync chain (st -> barrier -> issue -> commit -> mbarrier -> ld) is latency
+//     that only OTHER tile pipelines hide (measured: 2 pipelines per SM 0.97 ms, 4: 0.69 ms, 5: 0.60 ms; -61 % MMAs
+//     = -10 % time, -32 % epilogue instructions = -3 %, a quarter of the accumulator read = no change).  Tensor
+//     memory (512 columns) bounds the pipelines: 96 columns each (D 32, A_hi 32, A_lo 32; conv0's A overlays
+//     A_hi) + ONE constant block shared by all = five warpgroup pipelines in one persistent CTA per SM.
+// SASS: UTCHMMA / LDTM / STTM / UTCBAR (tcgen05.mma / .ld / .st / .commit).  The exact-FP32 kernel in cnn.cu
+// remains for other widths and as the in-library cross-check (RF_CNN_FP32=1).
 #include <cstdlib>
 
 #include "common.cuh"
