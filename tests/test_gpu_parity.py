@@ -81,6 +81,56 @@ def test_cnn_tensor_core_and_fp32_kernels_agree():
     assert np.abs(outs[1] - ref).max() < 5e-6 and np.abs(outs[0] - ref).max() < CNN_TIGHT
 
 
+class _SyntheticMLP(object):
+    """Random per-pixel MLP in the parameter layout of include/rf_b200.h (what caffe_model.PixelMLP provides)."""
+
+    def __init__(self, width, n_hidden, seed):
+        rng = np.random.default_rng(seed)
+        self.hidden, k = [], 3
+        for _ in range(n_hidden):
+            self.hidden.append((rng.normal(0, 1.2 / np.sqrt(k), (width, k)).astype(np.float32),
+                                rng.normal(0, 0.3, width).astype(np.float32)))
+            k = width
+        self.fuse_w = rng.normal(0, 0.5 / np.sqrt(width * n_hidden), width * n_hidden).astype(np.float32)
+        self.fuse_b = np.float32(0.1)
+
+    def flat_params(self):
+        parts = []
+        for w, b in self.hidden:
+            parts += [w.reshape(-1), b]
+        return np.ascontiguousarray(np.concatenate(parts + [self.fuse_w, np.asarray([self.fuse_b], np.float32)]))
+
+    def dims(self):
+        return [3] + [w.shape[0] for w, _ in self.hidden]
+
+
+@pytest.mark.parametrize("width,n_hidden", [(32, 2), (32, 3), (32, 8), (16, 4)])
+def test_cnn_other_depths_and_widths_through_the_c_abi(width, n_hidden):
+    """rf_cnn_create / rf_cnn_forward_u8 with graphs other than the shipped one: width 32 runs on the tensor
+    cores for 2..8 hidden layers (the bias row and conv0 planes are built per layer count), other widths on the
+    exact-FP32 kernel; both against the CPU oracle on a stress image with an odd pixel count."""
+    import ctypes as C
+    from reflectance_filtering_b200 import _native, device as dev
+    m = _SyntheticMLP(width, n_hidden, 17 * width + n_hidden)
+    params, dims = m.flat_params(), np.asarray(m.dims(), np.int32)
+    lut = np.ascontiguousarray(iu.srgb_lut(), np.float32)
+    handle = C.c_void_p()
+    _native.check(_native.lib().rf_cnn_create(params.ctypes.data_as(C.c_void_p), dims.ctypes.data_as(C.c_void_p),
+                                              len(dims) - 1, lut.ctypes.data_as(C.c_void_p), C.byref(handle)))
+    try:
+        img = synth.stress(61, 83, 5)
+        d = dev_u8(img[None])
+        out = torch.empty((1, 61, 83), dtype=torch.float32, device="cuda")
+        _native.check(_native.lib().rf_cnn_forward_u8(handle, dev.ptr(d), 1, 61, 83, dev.ptr(out), C.c_void_p(0),
+                                                      dev.stream_ptr()))
+        got = out.cpu().numpy()[0]
+    finally:
+        _native.lib().rf_cnn_destroy(handle)
+    ref = oracle.mlp_forward(m, img)
+    err = float(np.abs(got - ref).max())
+    assert err < CNN_TOL and err < 1e-4, err   # random weights: larger activations than the shipped model
+
+
 def test_cnn_fused_quantisation_is_truncation(net, mlp):
     imgs = synth.batch("natural", 3, 96, 80, 2)
     f32, u8 = net.forward_device(dev_u8(imgs), want_f32=True, want_u8=True)
