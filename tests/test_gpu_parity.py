@@ -295,6 +295,56 @@ def test_gf_full_size_three_iterations_and_properties(net):
     assert all(np.array_equal(o3[:, :, c], o1) for c in range(3))
 
 
+# ---- seeded random sweep: shapes, radii, channel combinations ------------------------------------------
+def test_random_sweep_bf_and_gf_against_the_oracle():
+    """48 seeded random cases through the device entry points against the CPU oracle: image sizes from 1 pixel
+    to a few strips wide (so strip / tile / row-segment boundaries land everywhere), radii below and above the
+    image size and on both sides of the fast-path limits, every joint/src channel combination, explicit d,
+    batches (batch == per-image), iterated guided filtering.  +-1 LSB everywhere."""
+    rng = np.random.default_rng(20260101)
+    worst = {"bf": (0, 0.0), "gf": (0, 0.0)}
+    for case in range(24):
+        h, w = int(rng.integers(1, 150)), int(rng.integers(1, 200))
+        jc, sc = int(rng.choice([1, 3])), int(rng.choice([1, 3]))
+        ss = float(rng.choice([0.4, 1.0, 2.7, 5.0, 9.3, 14.0, 22.0]))
+        scol = float(rng.choice([3.0, 8.0, 20.0, 60.0]))
+        d = int(rng.choice([-1, -1, 5, 12, 31]))
+        n = int(rng.integers(1, 4))
+        joint = np.stack([synth.natural(h, w, 9000 + 7 * case + i) for i in range(n)])
+        src = np.stack([synth.stress(h, w, 9500 + 7 * case + i) for i in range(n)])
+        joint = joint if jc == 3 else np.ascontiguousarray(joint[..., 0])
+        src = src if sc == 3 else np.ascontiguousarray(src[..., 0])
+        if case % 5 == 0:
+            joint = src.copy()
+            jc = sc
+        got = filters.joint_bilateral_device(dev_u8(joint), dev_u8(src), scol, ss, d=d).cpu().numpy()
+        for i in range(n):
+            ref = oracle.joint_bilateral(joint[i], src[i], d, scol, ss)
+            mx, frac = lsb_stats(got[i], ref.reshape(got[i].shape))
+            assert mx <= 1 and frac < 2e-3, ("bf", case, (n, h, w, jc, sc, ss, scol, d), mx, frac)
+            worst["bf"] = max(worst["bf"], (mx, frac))
+    for case in range(24):
+        h, w = int(rng.integers(1, 160)), int(rng.integers(1, 900 if case % 6 == 0 else 220))
+        sc = int(rng.choice([1, 3]))
+        r = int(rng.choice([1, 2, 5, 9, 17, 33, 45, 64, 65, 90]))
+        eps = float(rng.choice([0.005, 0.5, 3.0, 7.0, 50.0]))
+        iters = int(rng.choice([1, 1, 2, 3]))
+        n = int(rng.integers(1, 4))
+        guide = np.stack([synth.flat(h, w, 9900 + 5 * case + i) if case % 2 else synth.natural(h, w, 9900 + 5 * case + i)
+                          for i in range(n)])
+        src = np.stack([synth.natural(h, w, 9950 + 5 * case + i) for i in range(n)])
+        src = src if sc == 3 else np.ascontiguousarray(src[..., 0])
+        got = filters.guided_device(dev_u8(guide), dev_u8(src), r, eps, iterations=iters).cpu().numpy()
+        for i in range(n):
+            ref = src[i]
+            for _ in range(iters):
+                ref = oracle.guided(guide[i], ref, r, eps).reshape(src[i].shape)
+            mx, frac = lsb_stats(got[i], ref)
+            assert mx <= 1 and frac < 2e-3 * iters, ("gf", case, (n, h, w, sc, r, eps, iters), mx, frac)
+            worst["gf"] = max(worst["gf"], (mx, frac))
+    print("random sweep worst (max LSB, fraction differing):", worst)
+
+
 # ---- BASELINE configs 4 and 5 at full image size: oracle on crops ------------------------------------
 def _crop_regions(h, w, size):
     """(y0, y1, x0, x1) of the four corners (image borders included), two edge strips and one interior block."""
