@@ -93,10 +93,12 @@ int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t *src, int 
 int rf_joint_bilateral_geometry(double sigma_space, int d, int *radius, int *taps);
 int rf_joint_bilateral_max_radius(void);
 
-/* ---- guided filter, colour guide, 8-bit ----------------------------------------------------
- * guide [n][h][w][3], src / dst [n][h][w][sc], sc in {1, 3}.  Semantics of ximgproc guidedFilter
- * (He et al.) on the 0..255 scale: (2r+1)^2 box means with BORDER_REFLECT, cov(I) + eps * Id,
- * per-pixel 3x3 inverse, q = mean(a) . I + mean(b), output round-half-even saturated.
+/* ---- guided filter, 8-bit -------------------------------------------------------------------
+ * guide [n][h][w][gc], gc in {3, 1}; src / dst [n][h][w][sc], sc in {1, 3}.  Semantics of ximgproc
+ * guidedFilter (He et al.) on the 0..255 scale: (2r+1)^2 box means with BORDER_REFLECT, cov(I) + eps * Id,
+ * per-pixel 3x3 inverse (gc = 1: reciprocal of var(I) + eps), q = mean(a) . I + mean(b), output
+ * round-half-even saturated.  The reference CLI always passes a 3-channel guide (cv2.imread); 1-channel
+ * guides are the rest of the cv2.ximgproc.guidedFilter surface behind apply_filter.
  * A 1-channel src whose three channels would be equal (the CNN reflectance) is filtered once.
  * ws: caller-owned scratch of at least rf_guided_workspace_bytes(...) bytes. */
 size_t rf_guided_workspace_bytes(int sc, int n, int h, int w, int radius);

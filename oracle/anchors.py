@@ -86,6 +86,21 @@ def guided_cv2box(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: fl
     _need_cv2()
     f32 = np.float32
     eps = f32(eps)
+    if guide_u8.ndim == 2 or guide_u8.shape[2] == 1:  # 1-channel guide: scalar variance, reciprocal, multiply
+        I = guide_u8.reshape(guide_u8.shape[:2]).astype(f32)
+        src = src_u8 if src_u8.ndim == 3 else src_u8[:, :, None]
+        mean = lambda x: box_mean_cv2(x, radius)
+        mI = mean(I)
+        inv = f32(1.0) / ((mean(I * I) - mI * mI) + eps)
+        out = np.empty(src.shape, np.uint8)
+        for si in range(src.shape[2]):
+            p = src[:, :, si].astype(f32)
+            mp = mean(p)
+            al = (mean(p * I) - mp * mI) * inv
+            be = mp - al * mI
+            q = mean(be) + mean(al) * I
+            out[:, :, si] = np.clip(np.rint(q), 0, 255).astype(np.uint8)
+        return out if src_u8.ndim == 3 else out[:, :, 0]
     I = [guide_u8[:, :, c].astype(f32) for c in range(3)]
     src = src_u8 if src_u8.ndim == 3 else src_u8[:, :, None]
     mean = lambda x: box_mean_cv2(x, radius)

@@ -17,7 +17,7 @@
  *   orc_box_mean_reflect    cv::boxFilter(CV_32F, normalize, BORDER_REFLECT) as used by
  *                           ximgproc's guided filter (A.3 step 2)
  *   orc_guided_u8           cv2.ximgproc.guidedFilter call at filter_reflectance.py:67-70
- *                           (guided_filter.cpp, colour guide, A.3)
+ *                           (guided_filter.cpp, colour guide, A.3; and its 1-channel-guide case)
  *
  * Pinning (see oracle/README.md and tests/test_oracle_pins.py): the MLP is checked against
  * cv2.dnn reading the reference's own prototxt+caffemodel, the bilateral filter is
@@ -329,10 +329,55 @@ static void plane_from_u8(const uint8_t *img, int c, int cn, long n, float *out)
     for (long i = 0; i < n; ++i) out[i] = (float)img[i * cn + c];
 }
 
+/* 1-channel guide (guided_filter.cpp, gCnNum == 1; SURVEY A.3 "analogous special cases", [upstream-recollection]):
+ * the 1x1 "matrix" cov(I) + eps is inverted as a reciprocal, alpha = cov(I, p) * inv, beta = mean(p) - alpha * mean(I),
+ * q = mean(alpha) * I + mean(beta).  Not reachable from the reference CLI (cv2.imread hands it 3 channels); part of
+ * the cv2.ximgproc.guidedFilter surface behind apply_filter (filter_reflectance.py:67-70). */
+static int guided_gray_guide(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, int h, int w, int radius,
+                             float eps)
+{
+    const long n = (long)h * w;
+    enum { NPL = 8 };
+    float *buf = (float *)malloc(sizeof(float) * n * NPL);
+    float *acc = (float *)malloc(sizeof(float) * n * sc);
+    if (!buf || !acc) { free(buf); free(acc); return ORC_ENOMEM; }
+    float *I = buf, *mI = buf + n, *inv = buf + 2 * n, *tmp = buf + 3 * n, *p = buf + 4 * n, *mp = buf + 5 * n,
+          *a = buf + 6 * n, *b = buf + 7 * n;
+    int rc = ORC_OK;
+    plane_from_u8(guide, 0, 1, n, I);
+    rc |= orc_box_mean_reflect(I, mI, h, w, radius);
+    for (long i = 0; i < n; ++i) tmp[i] = I[i] * I[i];
+    rc |= orc_box_mean_reflect(tmp, inv, h, w, radius);
+    for (long i = 0; i < n; ++i) {
+        float v = inv[i] - mI[i] * mI[i];
+        v += eps;
+        inv[i] = 1.0f / v;
+    }
+    for (int si = 0; si < sc && rc == ORC_OK; ++si) {
+        plane_from_u8(src, si, sc, n, p);
+        rc |= orc_box_mean_reflect(p, mp, h, w, radius);
+        for (long i = 0; i < n; ++i) tmp[i] = p[i] * I[i];
+        rc |= orc_box_mean_reflect(tmp, a, h, w, radius);
+        for (long i = 0; i < n; ++i) {
+            float c = a[i] - mp[i] * mI[i];
+            float al = c * inv[i];
+            a[i] = al;
+            tmp[i] = mp[i] - al * mI[i];
+        }
+        rc |= orc_box_mean_reflect(tmp, b, h, w, radius);
+        rc |= orc_box_mean_reflect(a, tmp, h, w, radius);
+        for (long i = 0; i < n; ++i) acc[i * sc + si] = b[i] + tmp[i] * I[i];
+    }
+    for (long i = 0; i < n * sc; ++i) dst[i] = sat_u8(acc[i]);
+    free(buf); free(acc);
+    return rc;
+}
+
 int orc_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst,
                   int h, int w, int radius, double eps_d)
 {
-    if (gc != 3 || !(sc == 1 || sc == 3) || h < 1 || w < 1 || radius < 0) return ORC_EINVAL;
+    if (!(gc == 1 || gc == 3) || !(sc == 1 || sc == 3) || h < 1 || w < 1 || radius < 0) return ORC_EINVAL;
+    if (gc == 1) return guided_gray_guide(guide, src, sc, dst, h, w, radius, (float)eps_d);
     const long n = (long)h * w;
     const float eps = (float)eps_d;
     /* planes: I[3], mI[3], cov[6] -> inv[6], tmp, p, mp, c[3], a[3], b */

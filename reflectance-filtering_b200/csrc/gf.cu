@@ -80,30 +80,47 @@ __device__ __forceinline__ void block_scan_to_smem(T (&v)[Q], T *pref, T *wtot)
 }
 
 // ---- pass A --------------------------------------------------------------------------------------
-template <int SC>
+template <int GC>
+__host__ __device__ constexpr int n_quant(int sc) { return GC == 3 ? 9 + 4 * sc : 2 + 2 * sc; }
+
+// window quantities of one pixel.  Colour guide: I (3), I*I' (6), then per source channel p, p*I0, p*I1, p*I2.
+// 1-channel guide: I, I*I, then per source channel p, p*I.
+template <int SC, int GC>
 struct PixA {
-    uint32_t f[9 + 4 * SC];
+    uint32_t f[n_quant<GC>(SC)];
     __device__ __forceinline__ void load(const uint8_t *g, const uint8_t *s)
     {
-        const uint32_t i0 = g[0], i1 = g[1], i2 = g[2];
-        f[0] = i0; f[1] = i1; f[2] = i2;
-        f[3] = i0 * i0; f[4] = i0 * i1; f[5] = i0 * i2;
-        f[6] = i1 * i1; f[7] = i1 * i2; f[8] = i2 * i2;
+        if constexpr (GC == 3) {
+            const uint32_t i0 = g[0], i1 = g[1], i2 = g[2];
+            f[0] = i0; f[1] = i1; f[2] = i2;
+            f[3] = i0 * i0; f[4] = i0 * i1; f[5] = i0 * i2;
+            f[6] = i1 * i1; f[7] = i1 * i2; f[8] = i2 * i2;
 #pragma unroll
-        for (int c = 0; c < SC; ++c) {
-            const uint32_t p = s[c];
-            f[9 + 4 * c] = p;
-            f[10 + 4 * c] = p * i0;
-            f[11 + 4 * c] = p * i1;
-            f[12 + 4 * c] = p * i2;
+            for (int c = 0; c < SC; ++c) {
+                const uint32_t p = s[c];
+                f[9 + 4 * c] = p;
+                f[10 + 4 * c] = p * i0;
+                f[11 + 4 * c] = p * i1;
+                f[12 + 4 * c] = p * i2;
+            }
+        } else {
+            const uint32_t i0 = g[0];
+            f[0] = i0;
+            f[1] = i0 * i0;
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                const uint32_t p = s[c];
+                f[2 + 2 * c] = p;
+                f[3 + 2 * c] = p * i0;
+            }
         }
     }
 };
 
-template <int SC>
+template <int SC, int GC>
 __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
 {
-    constexpr int Q = 9 + 4 * SC;
+    constexpr int Q = n_quant<GC>(SC);
     extern __shared__ __align__(16) uint32_t sm_u32[];
     uint32_t *pref = sm_u32;              // [Q][NT + 1]
     uint32_t *wtot = pref + Q * (NT + 1); // [Q][NW]
@@ -118,7 +135,7 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
     const int xin = reflect(col, g.w);
     const bool is_out = tid >= r && tid < r + g.twa && col < g.w;
     const size_t img_px = (size_t)g.h * g.w;
-    const uint8_t *G = g.guide + img * img_px * 3 + (size_t)xin * 3;
+    const uint8_t *G = g.guide + img * img_px * GC + (size_t)xin * GC;
     const uint8_t *S = g.src + img * img_px * SC + (size_t)xin * SC;
 
     for (int q = tid; q < Q; q += NT) pref[q * (NT + 1)] = 0u;
@@ -129,8 +146,8 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
     if (col_active) {
         for (int dy = -r; dy < r; ++dy) {
             const size_t yy = (size_t)reflect(y0 + dy, g.h);
-            PixA<SC> px;
-            px.load(G + yy * g.w * 3, S + yy * g.w * SC);
+            PixA<SC, GC> px;
+            px.load(G + yy * g.w * GC, S + yy * g.w * SC);
 #pragma unroll
             for (int q = 0; q < Q; ++q) V[q] += px.f[q];
         }
@@ -138,8 +155,8 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
     for (int y = y0; y < y1; ++y) {
         if (col_active) {
             const size_t yy = (size_t)reflect(y + r, g.h);
-            PixA<SC> px;
-            px.load(G + yy * g.w * 3, S + yy * g.w * SC);
+            PixA<SC, GC> px;
+            px.load(G + yy * g.w * GC, S + yy * g.w * SC);
 #pragma unroll
             for (int q = 0; q < Q; ++q) V[q] += px.f[q];
         }
@@ -154,6 +171,19 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
                 const uint32_t s = pref[q * (NT + 1) + tid + r + 1] - pref[q * (NT + 1) + tid - r];
                 m[q] = (float)((double)s * g.scale);  // == cv::boxFilter's float(sum * scale)
             }
+            if constexpr (GC == 1) {
+                // 1-channel guide: the 1x1 inverse is a reciprocal, alpha = cov(I, p) * inv (oracle: guided_gray_guide)
+                const float var = __fadd_rn(__fsub_rn(m[1], __fmul_rn(m[0], m[0])), g.eps);
+                const float inv = __fdiv_rn(1.0f, var);
+#pragma unroll
+                for (int c = 0; c < SC; ++c) {
+                    const float mp = m[2 + 2 * c];
+                    const float k0 = __fsub_rn(m[3 + 2 * c], __fmul_rn(mp, m[0]));
+                    const float a0 = __fmul_rn(k0, inv);
+                    const float b = __fsub_rn(mp, __fmul_rn(a0, m[0]));
+                    g.ab[((size_t)(img * SC + c) * g.h + y) * g.w + col] = make_float4(a0, 0.0f, 0.0f, b);
+                }
+            } else {
             // cov(I) + eps on the diagonal; symmetric storage 0:(0,0) 1:(0,1) 2:(0,2) 3:(1,1) 4:(1,2) 5:(2,2)
             float c00 = __fadd_rn(__fsub_rn(m[3], __fmul_rn(m[0], m[0])), g.eps);
             float c01 = __fsub_rn(m[4], __fmul_rn(m[0], m[1]));
@@ -194,11 +224,12 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
                 b = __fsub_rn(b, __fmul_rn(a2, m[2]));
                 g.ab[((size_t)(img * SC + c) * g.h + y) * g.w + col] = make_float4(a0, a1, a2, b);
             }
+            }  // GC == 3
         }
         if (col_active) {
             const size_t yy = (size_t)reflect(y - r, g.h);
-            PixA<SC> px;
-            px.load(G + yy * g.w * 3, S + yy * g.w * SC);
+            PixA<SC, GC> px;
+            px.load(G + yy * g.w * GC, S + yy * g.w * SC);
 #pragma unroll
             for (int q = 0; q < Q; ++q) V[q] -= px.f[q];
         }
@@ -206,7 +237,7 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
 }
 
 // ---- pass B --------------------------------------------------------------------------------------
-template <int SC>
+template <int SC, int GC>
 __global__ void __launch_bounds__(NT) gf_pass_b(const Args g)
 {
     constexpr int Q = 4 * SC;
@@ -250,8 +281,8 @@ __global__ void __launch_bounds__(NT) gf_pass_b(const Args g)
         for (int q = 0; q < Q; ++q) Pq[q] = V[q];
         block_scan_to_smem<double, Q>(Pq, pref, wtot);
         if (is_out) {
-            const uint8_t *gp = g.guide + (img * img_px + (size_t)y * g.w + col) * 3;
-            const float i0 = gp[0], i1 = gp[1], i2 = gp[2];
+            const uint8_t *gp = g.guide + (img * img_px + (size_t)y * g.w + col) * GC;
+            const float i0 = gp[0], i1 = GC == 3 ? gp[GC - 2] : 0.0f, i2 = GC == 3 ? gp[GC - 1] : 0.0f;
             uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + col) * SC;
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
@@ -275,17 +306,17 @@ __global__ void __launch_bounds__(NT) gf_pass_b(const Args g)
 
 static size_t per_image_ws(int sc, int h, int w) { return (size_t)sc * h * w * sizeof(float4); }
 
-template <int SC>
+template <int SC, int GC>
 static int run(Args a, cudaStream_t st)
 {
-    const size_t smem_a = ((size_t)(9 + 4 * SC) * (NT + 1 + NW)) * sizeof(uint32_t);
+    const size_t smem_a = ((size_t)n_quant<GC>(SC) * (NT + 1 + NW)) * sizeof(uint32_t);
     const size_t smem_b = ((size_t)(4 * SC) * (NT + 1 + NW)) * sizeof(double);
     static bool configured[64] = {};
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_b<SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_b<SC, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured[dev & 63] = true;
     }
     const int max_twa = NT - 2 * a.r;
@@ -302,9 +333,9 @@ static int run(Args a, cudaStream_t st)
     }
     a.seg_rows = (a.h + segs - 1) / segs;
     dim3 grid(strips, (a.h + a.seg_rows - 1) / a.seg_rows, a.n);
-    gf_pass_a<SC><<<grid, NT, smem_a, st>>>(a);
+    gf_pass_a<SC, GC><<<grid, NT, smem_a, st>>>(a);
     RF_LAUNCH_CHECK("gf_pass_a");
-    gf_pass_b<SC><<<grid, NT, smem_b, st>>>(a);
+    gf_pass_b<SC, GC><<<grid, NT, smem_b, st>>>(a);
     RF_LAUNCH_CHECK("gf_pass_b");
     return RF_OK;
 }
@@ -362,7 +393,7 @@ static int guided_impl(const char *fn, const uint8_t *guide, int gc, const uint8
                        int h, int w, int radius, double eps, int iterations, void *ws, size_t ws_bytes, void *stream)
 {
     if (!guide || !src || !dst || !ws) return fail(RF_EINVAL, "%s: NULL pointer", fn);
-    if (gc != 3) return fail(RF_EUNSUPPORTED, "%s: only 3-channel guides are supported (got %d)", fn, gc);
+    if (!(gc == 1 || gc == 3)) return fail(RF_EINVAL, "%s: guide channels must be 1 or 3 (got %d)", fn, gc);
     if (!(sc == 1 || sc == 3)) return fail(RF_EINVAL, "%s: src channels must be 1 or 3 (got %d)", fn, sc);
     if (n < 0 || h < 1 || w < 1) return fail(RF_EINVAL, "%s: bad shape n=%d h=%d w=%d", fn, n, h, w);
     if (radius < 0) return fail(RF_EINVAL, "%s: negative radius", fn);
@@ -378,7 +409,8 @@ static int guided_impl(const char *fn, const uint8_t *guide, int gc, const uint8
     int chunk = (int)(ws_bytes / per < (size_t)n ? ws_bytes / per : (size_t)n);
     if (chunk > 65535) chunk = 65535;
     const size_t img_px = (size_t)h * w;
-    const bool generic = !gf2::supported(radius, h, w) || (flags_generic_path() != 0);
+    // 1-channel guides (not reachable from the reference CLI, which reads 3 channels) take the generic kernels
+    const bool generic = gc == 1 || !gf2::supported(radius, h, w) || (flags_generic_path() != 0);
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int nn = n - i0 < chunk ? n - i0 : chunk;
         if (!generic) {
@@ -395,7 +427,7 @@ static int guided_impl(const char *fn, const uint8_t *guide, int gc, const uint8
             uint8_t *out = ((iterations - 1 - it) & 1) ? tmp : dst + i0 * img_px * sc;
             gf::Args a;
             a.n = nn;
-            a.guide = guide + i0 * img_px * 3;
+            a.guide = guide + i0 * img_px * gc;
             a.src = in;
             a.dst = out;
             a.ab = (float4 *)ws;
@@ -406,7 +438,8 @@ static int guided_impl(const char *fn, const uint8_t *guide, int gc, const uint8
             a.scale = 1.0 / ((double)k * k);
             a.twa = 0;
             a.seg_rows = 0;
-            int rc = sc == 1 ? gf::run<1>(a, (cudaStream_t)stream) : gf::run<3>(a, (cudaStream_t)stream);
+            int rc = gc == 3 ? (sc == 1 ? gf::run<1, 3>(a, (cudaStream_t)stream) : gf::run<3, 3>(a, (cudaStream_t)stream))
+                             : (sc == 1 ? gf::run<1, 1>(a, (cudaStream_t)stream) : gf::run<3, 1>(a, (cudaStream_t)stream));
             if (rc != RF_OK) return rc;
             in = out;
         }

@@ -197,8 +197,6 @@ def apply_filter(filter_type, image, joint, sigma_color, sigma_spatial):
     timg = dev.to_device(img, "flt_img")[None]
     tjnt = timg if same else dev.to_device(jnt, "flt_jnt")[None]
 
-    if filter_type == 'guided' and jnt.shape[2] != 3:
-        raise ValueError("guided filter needs a 3-channel guidance image")
     src_gray = joint_gray = None
     if img.shape[2] == 3:
         flag = torch.ones(2, dtype=torch.int32, device=d)

@@ -234,6 +234,20 @@ def test_gf_matches_oracle(h, w, r, eps, sc):
     assert out.shape == ref.shape and mx <= 1 and frac < 2e-3, (mx, frac)
 
 
+@pytest.mark.parametrize("h,w,r,eps,sc", [(96, 120, 45, 3.0, 1), (72, 60, 7, 3.0, 3), (50, 610, 20, 0.5, 1), (1, 1, 1, 1.0, 3)])
+def test_gf_gray_guide_matches_oracle(h, w, r, eps, sc):
+    # 1-channel guide: device entry point and numpy operator (2-D joint), against the oracle; iterated == repeated
+    gd = np.ascontiguousarray(synth.flat(h, w, 61)[:, :, 2])
+    src = synth.natural(h, w, 62)
+    src = src if sc == 3 else np.ascontiguousarray(src[:, :, 0])
+    ref = oracle.guided(gd, src, r, eps)
+    out = filters.apply_filter("guided", src, gd, eps, float(r) + 0.3)
+    assert out.shape == ref.shape and np.array_equal(out, ref)      # the generic kernels are bit-equal to the oracle
+    dg, ds = dev_u8(gd[None]), dev_u8(src[None])
+    twice = filters.guided_device(dg, filters.guided_device(dg, ds, r, eps), r, eps)
+    assert torch.equal(filters.guided_device(dg, ds, r, eps, iterations=2), twice)
+
+
 @pytest.mark.parametrize("h,w,r,sc", [(33, 47, 7, 3), (33, 47, 7, 1), (40, 57, 12, 1), (64, 100, 20, 3)])
 def test_gf_ignores_workspace_contents(h, w, r, sc):
     # the workspace is scratch: results must not depend on what it held (regression: inf - inf in a prefix)

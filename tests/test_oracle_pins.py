@@ -123,6 +123,22 @@ def test_guided_matches_cv2box_restatement(r, eps, sc):
     assert (a != b).mean() < 1e-3
 
 
+@pytest.mark.parametrize("r,eps,sc", [(9, 3.0, 1), (45, 7.0, 3), (2, 0.5, 1)])
+def test_guided_gray_guide_matches_cv2box_restatement(r, eps, sc):
+    # 1-channel guide (the rest of the cv2.ximgproc.guidedFilter surface; not reachable from the reference CLI):
+    # two independent restatements, and the textbook identity GF_gray(I, p, eps) == p when p == I and eps -> 0
+    gd = synth.flat(64, 70, 41)[:, :, 1].copy()
+    src = synth.natural(64, 70, 42)
+    if sc == 1:
+        src = src[:, :, 0].copy()
+    a = oracle.guided(gd, src, r, eps)
+    b = anchors.guided_cv2box(gd, src, r, eps)
+    assert a.shape == src.shape and np.abs(a.astype(int) - b.astype(int)).max() <= 1
+    assert (a != b).mean() < 1e-3
+    self_guided = oracle.guided(gd, gd, r, 1e-4)
+    assert np.abs(self_guided.astype(int) - gd.astype(int)).max() <= 1
+
+
 def test_guided_properties():
     gd = synth.flat(48, 40, 41)
     const = np.full((48, 40, 3), 77, np.uint8)
