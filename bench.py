@@ -220,7 +220,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": mps, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -481,9 +481,23 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
                          # dram__bytes_read.sum + dram__bytes_write.sum of the seven launches at batch 64, from
                          # profiles/r01_gf3_ncu_full.txt (algorithmic: 3 x 40 B x 12.58 Mpx = 1.51 GB)
                          "traffic": 5150000000 if gf["batch"] == 64 else None, "peak_source": peak_src}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RECORD_FD = None
+
+
+def emit(line):
+    """The one JSON line of the run, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RECORD_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RECORD_FD, data)
 
 
 def main():
@@ -503,8 +517,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # stdout carries exactly ONE line (the JSON record of rank 0): NCCL's version / debug lines go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly ONE line (the JSON record of rank 0).  Native libraries print there too (NCCL's
+    # version banner at communicator creation), so file descriptor 1 is pointed at stderr for the run and the
+    # record is written to the saved descriptor at the end.
+    global _RECORD_FD
+    sys.stdout.flush()
+    _RECORD_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
     else:
