@@ -57,18 +57,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 // instruction descriptor: D=F32, A=B=TF32, both K-major, N=32, M=128
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((CW >> 3) << 17) | ((TILE_M >> 4) << 24);
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-
 // A operand from tensor memory (lanes = rows of the tile, one 32-bit column per TF32 element)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate)
 {
