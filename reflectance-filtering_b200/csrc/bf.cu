@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -137,7 +138,12 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
         const uint32_t *srow = ts + (ty + dyi) * a.pitch + a.rpad + x0;
         const float *trowA = tab + ady * 2 * a.tabw + a.rpad;  // E(dx), dx = index - 7 relative to qb
         const float *trowB = trowA + a.tabw;                   // the same row shifted by one entry
-        for (int qb = -w4; qb < P + w4; qb += 4) {
+        // one group of four neighbours (qb .. qb+3) against the outputs [PLO, PHI).  The first group of a row
+        // (qb = -w4) lies left of every window of outputs 4..7 and the last one (qb = P + w4 - 4) right of every
+        // window of outputs 0..3 (their table entries are +inf = weight exactly 0), so those halves are skipped:
+        // ~6 % fewer taps at r = 33, identical results.
+        auto quad = [&](const int qb, auto plo_c, auto phi_c) {
+            constexpr int PLO = decltype(plo_c)::value, PHI = decltype(phi_c)::value;
             const uint4 jn = *reinterpret_cast<const uint4 *>(jrow + qb);
             const uint4 sn = SEP ? *reinterpret_cast<const uint4 *>(srow + qb) : jn;
             const float4 a0 = *reinterpret_cast<const float4 *>(trowA + qb);
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
 #pragma unroll
             for (int jp = 0; jp < 4; jp += 2) {
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
+                for (int p = PLO; p < PHI; ++p) {
                     uint32_t d0, d1;
                     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d0) : "r"(jc[p]), "r"(jv[jp]), "r"(0x4B000000u));
                     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d1) : "r"(jc[p]), "r"(jv[jp + 1]), "r"(0x4B000000u));
@@ -180,7 +186,13 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
                     ffma2(acc23[p], ww1, r1[jp + 1]);
                 }
             }
-        }
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I4 = std::integral_constant<int, P / 2>;
+        using I8 = std::integral_constant<int, P>;
+        quad(-w4, I0{}, I4{});
+        for (int qb = -w4 + 4; qb < P + w4 - 4; qb += 4) quad(qb, I0{}, I8{});
+        quad(P + w4 - 4, I4{}, I8{});
     }
 
     const int gy = ty0 + ty;
