@@ -309,6 +309,22 @@ def test_gf_full_size_three_iterations_and_properties(net):
     assert all(np.array_equal(o3[:, :, c], o1) for c in range(3))
 
 
+def test_gf_self_guided_suggested_parameters(net):
+    """filter_reflectance.py:135-137 suggests `--filter_type=guided --sigma_color=7 --sigma_spatial=52` for filtering
+    the CNN prediction WITH ITSELF: guide = the gray reflectance PNG as cv2.imread returns it, three equal channels,
+    so cov(I) is singular and only eps*Id keeps the 3x3 inverse finite.  At the suggested eps the cofactor arithmetic
+    is still well inside FP32 and the result must be the oracle's, byte for byte up to rounding ties."""
+    img = synth.natural(384, 512, 8100)
+    r8 = (cnn.get_reflectance_caffe(net, img) * 255).astype(np.uint8)          # <base>-r.png
+    g3 = np.repeat(r8[:, :, None], 3, axis=2)                                    # cv2.imread of that PNG
+    for eps, ss in ((7.0, 52.0), (3.0, 45.0)):
+        out = filters.apply_filter("guided", g3, g3.copy(), eps, ss)
+        ref = oracle.guided(g3, g3, int(ss), eps)
+        mx, frac = lsb_stats(out, ref)
+        assert mx <= 1 and frac < 1e-3, (eps, ss, mx, frac)
+        assert np.array_equal(out[:, :, 0], out[:, :, 1]) and np.array_equal(out[:, :, 0], out[:, :, 2])
+
+
 # ---- seeded random sweep: shapes, radii, channel combinations ------------------------------------------
 def test_random_sweep_bf_and_gf_against_the_oracle():
     """48 seeded random cases through the device entry points against the CPU oracle: image sizes from 1 pixel
