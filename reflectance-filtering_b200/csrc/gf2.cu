@@ -149,27 +149,60 @@ __device__ __forceinline__ RowRaw<SC, C> prefetch_row(const uint32_t *plane0, si
     return r;
 }
 
+// (byte of pixel c, byte of pixel c+1) -> packed float pair, optionally negated: PRMT builds 2^23 + b in each half,
+// one packed add (or fused negate-add) removes the bias for both
+__device__ __forceinline__ unsigned long long b2f2(uint32_t w0, uint32_t w1, int byte, bool negate)
+{
+    const uint32_t sel = 0x7440u | (uint32_t)byte;
+    const unsigned long long p = pack2(__uint_as_float(__byte_perm(w0, 0x4B000000u, sel)),
+                                       __uint_as_float(__byte_perm(w1, 0x4B000000u, sel)));
+    unsigned long long r;
+    if (negate)
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p), "l"(pack2(-1.0f, -1.0f)), "l"(pack2(8388608.0f, 8388608.0f)));
+    else
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p), "l"(pack2(-8388608.0f, -8388608.0f)));
+    return r;
+}
+
+// Adds (sign = +1) or removes (sign = -1) one row: V[q][c] += sign * ch[qa] * ch[qb].  Two adjacent columns per packed
+// instruction (FADD2 / FFMA2 halve the issue slots of the conversion and of the accumulation; the FMA pipe does the
+// same work); the sign rides on the first factor, which is converted negated when a row leaves.  Exact: all values are
+// integers below 2^23.
 template <int SC, int C, int Q0, int NQ, int QBASE = 0>
 __device__ __forceinline__ void accumulate(float (&V)[NQG][C], const RowRaw<SC, C> &row, float sign)
 {
+    static_assert(C % 2 == 0, "column pairs");
+    const bool neg = sign < 0.0f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-        float ch[7];
-        ch[0] = b2f(row.w0[c], 0);
-        ch[1] = b2f(row.w0[c], 1);
-        ch[2] = b2f(row.w0[c], 2);
-        if (SC == 1) {
-            ch[3] = b2f(row.w0[c], 3);
-            ch[4] = 0.0f;
-            ch[5] = 0.0f;
-        } else {
-            ch[3] = b2f(row.w1[SC == 1 ? 0 : c], 0);
-            ch[4] = b2f(row.w1[SC == 1 ? 0 : c], 1);
-            ch[5] = b2f(row.w1[SC == 1 ? 0 : c], 2);
+    for (int c = 0; c < C; c += 2) {
+        // which channels this group needs as first factor (signed) and as second factor (plain)
+        bool need_a[6] = {false, false, false, false, false, false}, need_b[6] = {false, false, false, false, false, false};
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            need_a[qa(Q0 + q)] = true;
+            if (qb(Q0 + q) != 6) need_b[qb(Q0 + q)] = true;
         }
-        ch[6] = 1.0f;
+        unsigned long long sa[6], pb[6];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) V[q][c] = fmaf(sign * ch[qa(Q0 + q)], ch[qb(Q0 + q)], V[q][c]);
+        for (int k = 0; k < 6; ++k) {
+            const uint32_t w0 = k < 3 ? row.w0[c] : row.w1[SC == 1 ? 0 : c];
+            const uint32_t w1 = k < 3 ? row.w0[c + 1] : row.w1[SC == 1 ? 0 : c + 1];
+            const int byte = SC == 1 ? (k < 3 ? k : 3) : (k < 3 ? k : k - 3);
+            const bool live = SC == 3 || k <= 3;  // SC == 1: channels 4, 5 do not exist
+            const uint32_t x0 = (SC == 1 && k == 3) ? row.w0[c] : w0, x1 = (SC == 1 && k == 3) ? row.w0[c + 1] : w1;
+            sa[k] = pb[k] = 0ull;
+            if (live && need_a[k]) sa[k] = b2f2(x0, x1, byte, neg);
+            if (live && need_b[k]) pb[k] = (need_a[k] && !neg) ? sa[k] : b2f2(x0, x1, byte, false);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            unsigned long long v = pack2(V[q][c], V[q][c + 1]);
+            if (qb(Q0 + q) == 6)
+                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(v), "l"(sa[qa(Q0 + q)]));
+            else
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(v) : "l"(sa[qa(Q0 + q)]), "l"(pb[qb(Q0 + q)]));
+            unpack2(v, V[q][c], V[q][c + 1]);
+        }
     }
 }
 
