@@ -215,9 +215,16 @@ __device__ __forceinline__ void scan_store(const float (&V)[NQG][C], uint32_t *P
         uint32_t pre[C];
         uint32_t run = 0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            run += __float_as_uint(V[q][c] + 8388608.0f);  // integer value + 0x4B000000 per element
+        for (int c = 0; c < C; c += 2) {
+            // integer value + 0x4B000000 per element; the float add on two columns at once
+            unsigned long long b2;
+            asm("add.rn.f32x2 %0, %1, %2;" : "=l"(b2) : "l"(pack2(V[q][c], V[q][c + 1])), "l"(pack2(8388608.0f, 8388608.0f)));
+            float b0, b1;
+            unpack2(b2, b0, b1);
+            run += __float_as_uint(b0);
             pre[c] = run;
+            run += __float_as_uint(b1);
+            pre[c + 1] = run;
         }
         uint32_t incl = run;
 #pragma unroll
@@ -515,9 +522,13 @@ __global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
         }
         return k;
     };
-    auto add = [&](const Chunk &k, float sign) {
+    auto add = [&](const Chunk &k, float sign) {  // exact either way: sign * x is x or -x
 #pragma unroll
-        for (int c = 0; c < C; ++c) V[c] = fmaf(sign, k.v[c], V[c]);
+        for (int c = 0; c < C; c += 2) {
+            unsigned long long v = pack2(V[c], V[c + 1]);
+            ffma2(v, pack2(sign, sign), pack2(k.v[c], k.v[c + 1]));
+            unpack2(v, V[c], V[c + 1]);
+        }
     };
     // Rows are loaded into registers PF steps ahead of their use.  Measured on B200 (64 x 512 x 384, r = 45):
     // PF = 3 costs occupancy (128 registers) and is 35 % slower; an additional prefetch.global.L2 eight rows
