@@ -479,8 +479,9 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
                          "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "bytes_per_pixel_per_iteration": bpp,
                          "launch_ms": gf["gf_x3_ms"], "single_iteration_call_ms": gf["gf_iteration_ms"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of the seven launches at batch 64, from
-                         # profiles/r01_gf3_ncu_full.txt (algorithmic: 3 x 40 B x 12.58 Mpx = 1.51 GB)
-                         "traffic": 5150000000 if gf["batch"] == 64 else None, "peak_source": peak_src}}
+                         # profiles/r01_gf_v8_ncu_full.txt: pass A<full+stats> 765 MB, pass B 856 MB, 2 x (pass A<source
+                         # only> 807 MB + pass B 856 MB), pack ~0.11 GB (algorithmic: 3 x 40 B x 12.58 Mpx = 1.51 GB)
+                         "traffic": 5060000000 if gf["batch"] == 64 else None, "peak_source": peak_src}}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
