@@ -75,6 +75,40 @@ def bilateral_self(image_u8: np.ndarray, sigma_color: float, sigma_space: float)
     return cv2.bilateralFilter(image_u8, -1, float(sigma_color), float(sigma_space))
 
 
+def joint_bilateral_numpy(joint_u8: np.ndarray, src_u8: np.ndarray, d: int, sigma_color: float,
+                          sigma_space: float) -> np.ndarray:
+    """SURVEY A.2 (jointBilateralFilter_8u) written independently of oracle/rf_oracle.c: cv2.copyMakeBorder for the
+    REFLECT_101 padding, numpy float32 arithmetic vectorised over the image, taps accumulated in the same raster
+    order one at a time.  For joint != src, where cv2.bilateralFilter cannot serve as the anchor."""
+    _need_cv2()
+    f32 = np.float32
+    joint = joint_u8 if joint_u8.ndim == 3 else joint_u8[:, :, None]
+    src = src_u8 if src_u8.ndim == 3 else src_u8[:, :, None]
+    h, w = src.shape[:2]
+    sigma_color = sigma_color if sigma_color > 0 else 1.0
+    sigma_space = sigma_space if sigma_space > 0 else 1.0
+    radius = max(int(np.rint(sigma_space * 1.5)) if d <= 0 else d // 2, 1)   # cvRound = round-half-even
+    cw = np.exp(np.arange(256 * joint.shape[2], dtype=np.float64) ** 2 * (-0.5 / sigma_color ** 2)).astype(f32)
+    pad = lambda a: cv2.copyMakeBorder(a, radius, radius, radius, radius, cv2.BORDER_REFLECT_101).reshape(
+        a.shape[0] + 2 * radius, a.shape[1] + 2 * radius, -1)
+    pj, ps = pad(np.ascontiguousarray(joint)).astype(np.int32), pad(np.ascontiguousarray(src)).astype(f32)
+    j0 = pj[radius:radius + h, radius:radius + w]
+    acc = np.zeros((h, w, src.shape[2]), f32)
+    wsum = np.zeros((h, w), f32)
+    for i in range(-radius, radius + 1):
+        for j in range(-radius, radius + 1):
+            if i * i + j * j > radius * radius:
+                continue
+            sw = f32(np.exp((i * i + j * j) * (-0.5 / sigma_space ** 2)))
+            jk = pj[radius + i:radius + i + h, radius + j:radius + j + w]
+            alpha = np.abs(j0 - jk).sum(axis=2)
+            wt = sw * cw[alpha]
+            acc += wt[:, :, None] * ps[radius + i:radius + i + h, radius + j:radius + j + w]
+            wsum += wt
+    out = np.clip(np.rint(acc / wsum[:, :, None]), 0, 255).astype(np.uint8)
+    return out if src_u8.ndim == 3 else out[:, :, 0]
+
+
 def box_mean_cv2(plane_f32: np.ndarray, r: int) -> np.ndarray:
     _need_cv2()
     k = 2 * int(r) + 1

@@ -104,6 +104,20 @@ def test_joint_bilateral_live_anchor_and_properties():
     assert np.array_equal(o[:, :, 0], o[:, :, 1]) and np.array_equal(o[:, :, 0], o[:, :, 2])
 
 
+@pytest.mark.parametrize("jc,sc,scol,ss,d", [(3, 3, 20.0, 6.0, -1), (3, 1, 12.0, 4.0, -1), (1, 3, 30.0, 3.0, 9),
+                                              (1, 1, 8.0, 5.0, -1)])
+def test_joint_bilateral_distinct_joint_matches_numpy_restatement(jc, sc, scol, ss, d):
+    # joint != src is the one bilateral case cv2.bilateralFilter cannot anchor: a second, independently written
+    # restatement (numpy on cv2.copyMakeBorder, float32, same tap order) must give the same bytes
+    joint = synth.natural(37, 45, 71)
+    src = synth.stress(37, 45, 72)
+    joint = joint if jc == 3 else np.ascontiguousarray(joint[:, :, 1])
+    src = src if sc == 3 else np.ascontiguousarray(src[:, :, 2])
+    a = oracle.joint_bilateral(joint, src, d, scol, ss).reshape(src.shape)
+    b = anchors.joint_bilateral_numpy(joint, src, d, scol, ss)
+    assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("r", [1, 7, 45])
 def test_box_mean_bit_exact_vs_cv2(G, r):
     assert np.array_equal(oracle.box_mean_reflect(G["box_in"], r), G["box_r%d" % r])
