@@ -115,6 +115,13 @@ int rf_guided_iterated_u8(const uint8_t *guide, int gc, const uint8_t *src, int 
                           int h, int w, int radius, double eps, int iterations, void *ws, size_t ws_bytes,
                           void *stream);
 
+/* Diagnostic: the row plan of the guided filter's second pass for output row y.  The first pass stores, per
+ * coefficient plane, prefix sums down the image rows that restart every seg_rows rows; the (2*radius+1)-row window
+ * sum of row y under BORDER_REFLECT is sum_i weights[i] * prefix_row[rows[i]].  rows / weights hold at least 12
+ * entries; returns the number of terms (more than 12: this segmentation is not used), -1 on bad arguments.
+ * Host-only, no CUDA call (lets CPU tests check the decomposition against a brute-force window sum). */
+int rf_guided_row_terms(int h, int radius, int seg_rows, int y, int *rows, float *weights);
+
 /* ---- layout helpers ------------------------------------------------------------------------ */
 /* gray [n_px] -> bgr [n_px][3] with three equal channels (what cv2.imread returns for the CNN PNG) */
 int rf_replicate_gray_u8(const uint8_t *gray, uint8_t *bgr, size_t n_px, void *stream);

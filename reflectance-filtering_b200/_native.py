@@ -38,6 +38,7 @@ SIGNATURES = {
     "rf_guided_max_radius": (_i, []),
     "rf_guided_iterated_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "rf_guided_iterated_u8": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _d, _i, _vp, _sz, _vp]),
+    "rf_guided_row_terms": (_i, [_i, _i, _i, _i, _ip, C.POINTER(C.c_float)]),
     "rf_replicate_gray_u8": (_i, [_vp, _vp, _sz, _vp]),
     "rf_extract_gray_u8": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "rf_accumulate_stats_u8": (_i, [_vp, _vp, _sz, _vp, _vp]),

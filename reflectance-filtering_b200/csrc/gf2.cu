@@ -8,25 +8,41 @@
 //   * a pack kernel writes guide + source once as 32-bit pixels (B | G<<8 | R<<16 | p<<24) into planes
 //     that are padded by the halo with BORDER_REFLECT columns already resolved: every later load is an
 //     aligned 128-bit load of four pixels, with no border case in x (rows reflect by index);
-//   * every lane owns C consecutive columns of a 32*C wide strip and keeps the vertical window sums of
+//   * pass A: every lane owns C consecutive columns of a 32*C wide strip and keeps the vertical window sums of
 //     its quantities in FP32 registers -- integers below 2^23 ((2r+1)*255^2 for r <= 64), so the FFMA
 //     updates (add the entering row, subtract the leaving one) are exact;
 //   * the horizontal direction is a per-lane serial prefix over its C columns plus ONE 5-step warp scan
 //     of the lane totals per quantity (uint32, wrap-around safe): 5/C shuffles per column;
 //   * the 9 + 4*SC quantities are split over the warps of the CTA (each warp scans the whole strip for
 //     its 3-4 quantities); prefixes go to a double-buffered shared-memory row, and after ONE
-//     __syncthreads per row all threads turn P[x+r] - P[x-r-1] into means, solve the 3x3 system with
-//     the oracle's non-contracted multiply/add order and store the coefficient planes (again padded,
-//     border pixels mirrored into the halo so pass B has no border case either);
+//     __syncthreads per row every thread turns P[x+r] - P[x-r-1] of ONE PIXEL PAIR into means and solves the
+//     two 3x3 systems as one packed (f32x2) instruction stream, in the oracle's non-contracted multiply/add
+//     order;
+//   * pass A does not store the coefficients (a0, a1, a2, b) themselves but their VERTICAL PREFIX SUM down the
+//     rows of its row segment (a thread owns the same columns in every row, so this is one packed add per
+//     coefficient).  That makes pass B row-independent: the vertical window sum of a coefficient plane is a
+//     signed sum of 2-4 prefix rows (row_terms() below: PV[y+r] - PV[y-r-1], plus the totals of segments the
+//     window crosses and the BORDER_REFLECT mirror parts), so pass B has no sliding state, no warm-up rows and
+//     no leaving-row stream, and every prefix row is read from DRAM once (its second use, 2r+1 rows later, hits
+//     L2 because the grid walks the rows in order);
+//   * pass B: one warp per (output row, coefficient plane); the prefix rows arrive in shared memory through
+//     TMA (cp.async.bulk.tensor on a 3-D map of the planes, two slots per warp, mbarrier completion; columns
+//     beyond the padded row are zero-filled by the hardware), the warp sums its terms, runs the same
+//     per-lane prefix + warp scan over the row in FP32, and after one __syncthreads the threads of the row
+//     combine the four box means with the guide of one pixel pair each (packed arithmetic) and store uint8;
 //   * no FP64: the box mean is float(S) * float(1/k^2) (<= 1 ulp from OpenCV's float(double(S)/k^2);
-//     measured effect ~2.5e-5 of the output bytes move by 1 LSB); pass B accumulates the
-//     coefficient planes in FP32 the same way;
+//     measured effect ~2.5e-5 of the output bytes move by 1 LSB);
 //   * iterated filtering with one guide (createGuidedFilter(guide, r, eps) reused for several filter() calls,
 //     SURVEY 8f-4; the "3 x GF" configuration): the first pass A also stores mean(I) and the inverse
 //     covariance per pixel, later iterations only accumulate the 4*SC source quantities and read those nine
 //     floats back; pass B writes its uint8 output straight into the packed planes, so later iterations need
 //     no pack kernel.  The arithmetic per pixel is the same function in both modes: results are byte-identical
 //     to repeated single calls.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -37,24 +53,120 @@ namespace gf2 {
 constexpr int MAX_RADIUS = 64;  // (2r+1) * 65025 < 2^23
 constexpr int QMAX = 21;
 
+constexpr int MAXT = 12;                  // most prefix rows one window sum needs (row_terms)
+constexpr int PLAN_STRIDE = 2 * MAXT + 4;  // ints per row of the row plan: count, pad, pad, pad, rows, weights
+
 struct Args {
     const uint8_t *guide;  // [n][h][w][3]
     const uint8_t *src;    // [n][h][w][SC]
     uint32_t *packed;      // [n][NP][h][wp]  NP = 1 (SC == 1: B,G,R,p) or 2 (SC == 3: B,G,R,0 / p0,p1,p2,0)
-    float *ab;             // [n][SC][4][h][wp]  (a0, a1, a2, b), columns padded like `packed`
+    float *ab;             // [n][SC][4][h][wp]  vertical prefix sums (restarted every seg_rows rows) of
+                           // (a0, a1, a2, b), columns padded like `packed`
     float *gstat;          // [n][9][h][wp]  guide statistics kept for iterated filtering: mean I (3) and the
                            // inverse of cov(I) + eps*Id (00, 01, 02, 11, 12, 22); NULL when not wanted
+    const int *plan;       // [h][PLAN_STRIDE]  row plan of pass B (plan_kernel)
     uint8_t *dst;          // [n][h][w][SC]
     int store_dst;         // pass B writes dst (last iteration)
     int store_packed;      // pass B writes its output into the source bytes of `packed` (input of the next iteration)
     int n, h, w, r;
     int rh;          // halo columns on each side: round_up(r + 1, 4)
     int wp;          // padded row pitch in pixels: round_up(w + 2 * rh + 16, 4)
-    int twe;         // output columns per strip (multiple of 4)
-    int seg_rows;    // output rows per CTA
+    int twe;         // pass A: output columns per strip (multiple of 4)
+    int seg_rows;    // pass A: output rows per CTA = rows per prefix segment
+    int twe_b;       // pass B: output columns per strip (multiple of 4)
     float eps;
     float inv_area;  // 1 / (2r+1)^2
 };
+
+// ---- packed FP32 pairs (one 64-bit register = two adjacent pixels) ---------------------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b)
+{
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 dup2(float v) { return pack2(v, v); }
+
+// ---- row plan of pass B ------------------------------------------------------------------------------
+// Pass A stores PV[y] = sum of the coefficient rows seg_start(y) .. y (the prefix restarts at every multiple of
+// seg_rows).  The vertical window sum of output row y -- rows y-r .. y+r under BORDER_REFLECT
+// (fedcba|abcdefgh|hgfedcb) -- is then a signed sum of a few prefix rows.
+struct RowTerms {
+    int cnt;  // > MAXT: does not fit (never for h > r and seg_rows >= 64)
+    int row[MAXT];
+    float wgt[MAXT];
+};
+
+__host__ __device__ inline void push_term(RowTerms &t, int row, float w)
+{
+    for (int i = 0; i < t.cnt && i < MAXT; ++i)
+        if (t.row[i] == row) {
+            t.wgt[i] += w;
+            return;
+        }
+    if (t.cnt < MAXT) {
+        t.row[t.cnt] = row;
+        t.wgt[t.cnt] = w;
+    }
+    ++t.cnt;
+}
+
+// image rows lo .. hi (0 <= lo <= hi < h)
+__host__ __device__ inline void add_range(RowTerms &t, int lo, int hi, int seg_rows)
+{
+    push_term(t, hi, 1.0f);
+    int s = (hi / seg_rows) * seg_rows;  // first row of hi's segment
+    while (s > lo) {                     // the range reaches into the previous segment: add that segment's total
+        push_term(t, s - 1, 1.0f);
+        s -= seg_rows;
+    }
+    if (lo > s) push_term(t, lo - 1, -1.0f);
+}
+
+__host__ __device__ inline void row_terms(RowTerms &t, int y, int h, int r, int seg_rows)
+{
+    t.cnt = 0;
+    int p = y - r;
+    const int end = y + r;
+    while (p <= end) {
+        const int m = p >= 0 ? p / h : -((-p + h - 1) / h);  // which reflected copy of the image p falls into
+        const int q = p - m * h;
+        const int rest = end - p + 1;
+        const int len = h - q < rest ? h - q : rest;
+        if ((m & 1) == 0)
+            add_range(t, q, q + len - 1, seg_rows);  // upright copy
+        else
+            add_range(t, h - q - len, h - 1 - q, seg_rows);  // mirrored copy
+        p += len;
+    }
+}
+
+__global__ void plan_kernel(int *plan, int h, int r, int seg_rows)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= h) return;
+    RowTerms t;
+    row_terms(t, y, h, r, seg_rows);
+    int *o = plan + (size_t)y * PLAN_STRIDE;
+    o[0] = t.cnt < MAXT ? t.cnt : MAXT;
+    for (int i = 0; i < MAXT; ++i) {
+        o[4 + i] = i < t.cnt ? t.row[i] : 0;
+        o[4 + MAXT + i] = __float_as_int(i < t.cnt ? t.wgt[i] : 0.0f);
+    }
+}
 
 __device__ __forceinline__ float b2f(uint32_t word, int byte)
 {
@@ -286,77 +398,102 @@ __host__ __device__ constexpr int n_groups() { return SC == 1 ? 4 : 6; }
 
 enum Mode { FULL = 0, FULL_STORE = 1, SRC_ONLY = 2 };
 
-// window sum -> box mean.  Sums of single channels stay below 2^23: exact integer->float on the FMA pipe.
-__device__ __forceinline__ float box_mean(uint32_t s, bool linear, float inv_area)
+// window sums of the pixel pair (i, i+1) -> box means.  Sums of single channels stay below 2^23: exact
+// integer->float on the FMA pipe.  (Four 32-bit loads: which of the two index pairs is 8-byte aligned depends on
+// the parity of the radius.)
+__device__ __forceinline__ f2 box_mean2(const uint32_t *Pq, int i, int r, uint32_t bias, bool linear, f2 inv_area2)
 {
-    const float sf = linear ? __uint_as_float(s | 0x4B000000u) - 8388608.0f : (float)s;
-    return __fmul_rn(sf, inv_area);
+    const uint32_t d0 = Pq[i + r] - Pq[i - r - 1] - bias, d1 = Pq[i + r + 1] - Pq[i - r] - bias;
+    f2 sf;
+    if (linear)
+        sf = add2(pack2(__uint_as_float(d0 | 0x4B000000u), __uint_as_float(d1 | 0x4B000000u)), dup2(-8388608.0f));
+    else
+        sf = pack2((float)d0, (float)d1);
+    return mul2(sf, inv_area2);
 }
 
-// inverse of cov(I) + eps*Id from the nine guide means m[0..8]; out: inv 00, 01, 02, 11, 12, 22
-__device__ __forceinline__ void guide_inverse(const float *m, float eps, float *inv)
+// inverse of cov(I) + eps*Id from the nine guide means m[0..8]; out: inv 00, 01, 02, 11, 12, 22.  Two pixels per
+// instruction; every step is the separately rounded multiply / add / subtract of the oracle.
+__device__ __forceinline__ void guide_inverse2(const f2 *m, float eps, f2 *inv)
 {
+    const f2 e2 = dup2(eps);
     // cov(I) + eps*Id, symmetric storage 0:(0,0) 1:(0,1) 2:(0,2) 3:(1,1) 4:(1,2) 5:(2,2)
-    const float c00 = __fadd_rn(__fsub_rn(m[3], __fmul_rn(m[0], m[0])), eps);
-    const float c01 = __fsub_rn(m[4], __fmul_rn(m[0], m[1]));
-    const float c02 = __fsub_rn(m[5], __fmul_rn(m[0], m[2]));
-    const float c11 = __fadd_rn(__fsub_rn(m[6], __fmul_rn(m[1], m[1])), eps);
-    const float c12 = __fsub_rn(m[7], __fmul_rn(m[1], m[2]));
-    const float c22 = __fadd_rn(__fsub_rn(m[8], __fmul_rn(m[2], m[2])), eps);
-    const float f00 = __fsub_rn(__fmul_rn(c11, c22), __fmul_rn(c12, c12));
-    const float f01 = __fsub_rn(__fmul_rn(c12, c02), __fmul_rn(c01, c22));
-    const float f02 = __fsub_rn(__fmul_rn(c01, c12), __fmul_rn(c11, c02));
-    const float f11 = __fsub_rn(__fmul_rn(c22, c00), __fmul_rn(c02, c02));
-    const float f12 = __fsub_rn(__fmul_rn(c02, c01), __fmul_rn(c12, c00));
-    const float f22 = __fsub_rn(__fmul_rn(c00, c11), __fmul_rn(c01, c01));
-    float det = __fmul_rn(c00, f00);
-    det = __fadd_rn(det, __fmul_rn(c01, f01));
-    det = __fadd_rn(det, __fmul_rn(c02, f02));
-    if (eps < 1e-2f && fabsf(det) < 1e-6f) det = 1e-6f;
+    const f2 c00 = add2(sub2(m[3], mul2(m[0], m[0])), e2);
+    const f2 c01 = sub2(m[4], mul2(m[0], m[1]));
+    const f2 c02 = sub2(m[5], mul2(m[0], m[2]));
+    const f2 c11 = add2(sub2(m[6], mul2(m[1], m[1])), e2);
+    const f2 c12 = sub2(m[7], mul2(m[1], m[2]));
+    const f2 c22 = add2(sub2(m[8], mul2(m[2], m[2])), e2);
+    const f2 f00 = sub2(mul2(c11, c22), mul2(c12, c12));
+    const f2 f01 = sub2(mul2(c12, c02), mul2(c01, c22));
+    const f2 f02 = sub2(mul2(c01, c12), mul2(c11, c02));
+    const f2 f11 = sub2(mul2(c22, c00), mul2(c02, c02));
+    const f2 f12 = sub2(mul2(c02, c01), mul2(c12, c00));
+    const f2 f22 = sub2(mul2(c00, c11), mul2(c01, c01));
+    f2 det = mul2(c00, f00);
+    det = add2(det, mul2(c01, f01));
+    det = add2(det, mul2(c02, f02));
+    float d0, d1;
+    unpack2(det, d0, d1);
+    if (eps < 1e-2f) {
+        if (fabsf(d0) < 1e-6f) d0 = 1e-6f;
+        if (fabsf(d1) < 1e-6f) d1 = 1e-6f;
+    }
     // one correctly rounded reciprocal instead of six divisions: each entry is within 1 ulp of cof/det
-    const float rdet = __frcp_rn(det);
-    inv[0] = __fmul_rn(f00, rdet);
-    inv[1] = __fmul_rn(f01, rdet);
-    inv[2] = __fmul_rn(f02, rdet);
-    inv[3] = __fmul_rn(f11, rdet);
-    inv[4] = __fmul_rn(f12, rdet);
-    inv[5] = __fmul_rn(f22, rdet);
+    const f2 rdet = pack2(__frcp_rn(d0), __frcp_rn(d1));
+    inv[0] = mul2(f00, rdet);
+    inv[1] = mul2(f01, rdet);
+    inv[2] = mul2(f02, rdet);
+    inv[3] = mul2(f11, rdet);
+    inv[4] = mul2(f12, rdet);
+    inv[5] = mul2(f22, rdet);
 }
 
 // a = inv * (mean(I p) - mean(I) mean(p)),  b = mean(p) - a . mean(I);  ms = (mean p, mean p*I0, p*I1, p*I2)
-__device__ __forceinline__ void solve_source(const float *ms, const float *mi, const float *inv, float *v)
+__device__ __forceinline__ void solve_source2(const f2 *ms, const f2 *mi, const f2 *inv, f2 *v)
 {
-    const float mp = ms[0];
-    const float k0 = __fsub_rn(ms[1], __fmul_rn(mp, mi[0]));
-    const float k1 = __fsub_rn(ms[2], __fmul_rn(mp, mi[1]));
-    const float k2 = __fsub_rn(ms[3], __fmul_rn(mp, mi[2]));
-    float a0 = __fmul_rn(inv[0], k0);
-    a0 = __fadd_rn(a0, __fmul_rn(inv[1], k1));
-    a0 = __fadd_rn(a0, __fmul_rn(inv[2], k2));
-    float a1 = __fmul_rn(inv[1], k0);
-    a1 = __fadd_rn(a1, __fmul_rn(inv[3], k1));
-    a1 = __fadd_rn(a1, __fmul_rn(inv[4], k2));
-    float a2 = __fmul_rn(inv[2], k0);
-    a2 = __fadd_rn(a2, __fmul_rn(inv[4], k1));
-    a2 = __fadd_rn(a2, __fmul_rn(inv[5], k2));
-    float b = __fsub_rn(mp, __fmul_rn(a0, mi[0]));
-    b = __fsub_rn(b, __fmul_rn(a1, mi[1]));
-    b = __fsub_rn(b, __fmul_rn(a2, mi[2]));
+    const f2 mp = ms[0];
+    const f2 k0 = sub2(ms[1], mul2(mp, mi[0]));
+    const f2 k1 = sub2(ms[2], mul2(mp, mi[1]));
+    const f2 k2 = sub2(ms[3], mul2(mp, mi[2]));
+    f2 a0 = mul2(inv[0], k0);
+    a0 = add2(a0, mul2(inv[1], k1));
+    a0 = add2(a0, mul2(inv[2], k2));
+    f2 a1 = mul2(inv[1], k0);
+    a1 = add2(a1, mul2(inv[3], k1));
+    a1 = add2(a1, mul2(inv[4], k2));
+    f2 a2 = mul2(inv[2], k0);
+    a2 = add2(a2, mul2(inv[4], k1));
+    a2 = add2(a2, mul2(inv[5], k2));
+    f2 b = sub2(mp, mul2(a0, mi[0]));
+    b = sub2(b, mul2(a1, mi[1]));
+    b = sub2(b, mul2(a2, mi[2]));
     v[0] = a0;
     v[1] = a1;
     v[2] = a2;
     v[3] = b;
 }
 
+// stores a pixel pair (8-byte aligned address), or only its first pixel when the second lies outside the image
+__device__ __forceinline__ void st_pair(float *p, f2 v, bool both)
+{
+    if (both) {
+        *reinterpret_cast<f2 *>(p) = v;
+    } else {
+        float lo, hi;
+        unpack2(v, lo, hi);
+        *p = lo;
+    }
+}
+
 // ---- pass A ---------------------------------------------------------------------------------------
 // MODE FULL: all 9 + 4*SC quantities.  FULL_STORE: the same, and the guide statistics go to g.gstat.
 // SRC_ONLY: only the 4*SC source quantities; mean(I) and the inverse covariance come from g.gstat.
 template <int SC, int C, int MODE>
-__global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args g)
+__global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1) pass_a_kernel(const Args g)
 {
-    constexpr int QB = MODE == SRC_ONLY ? 9 : 0;           // first quantity this kernel accumulates
+    constexpr int QB = MODE == SRC_ONLY ? 9 : 0;  // first quantity this kernel accumulates
     constexpr int Q = 9 + 4 * SC - QB, NX = 32 * C, NT = 32 * n_groups<SC>(), NP = SC == 1 ? 1 : 2;
-    constexpr int MAXPX = (NX + NT - 1) / NT;  // output pixels a thread solves per row, at most
     extern __shared__ __align__(16) uint32_t pbuf[];  // [2][Q][NX]
     const int tid = threadIdx.x, lane = tid & 31, group = tid >> 5;
     const int img = blockIdx.z;
@@ -366,13 +503,14 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
     const size_t plane = (size_t)g.h * g.wp;
     const uint32_t *PK = g.packed + (size_t)img * NP * plane;
     const int r = g.r;
-    const int n_out = min(g.twe, g.w - sx0);
+    const int n_out = min(g.twe, g.w - sx0);  // <= 2 * NT: every thread solves at most one pixel pair per row
     const uint32_t bias = (uint32_t)(2 * r + 1) * 0x4B000000u;  // what the biased elements add to a window
     // padded coordinate of this lane's first column is sx0 + lane*C (strip origin sx0 - rh, plus the rh
     // offset of the padding).  Lanes whose chunk would start beyond the padded row re-read the last
     // chunk: their prefixes lie right of every window of this strip and are never used.
     const int xp0c = min(sx0 + lane * C, g.wp - C);
     float *GS = MODE == FULL ? nullptr : g.gstat + (size_t)img * 9 * plane;
+    const f2 ia2 = dup2(g.inv_area);
 
     float V[NQG][C];
 #pragma unroll
@@ -380,67 +518,85 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
 #pragma unroll
         for (int c = 0; c < C; ++c) V[q][c] = 0.0f;
 
+    // this thread's pixel pair: output columns sx0 + idx, sx0 + idx + 1 of every row of the segment
+    const int idx = 2 * tid;
+    const bool active = idx < n_out;
+    const bool both = idx + 1 < n_out;  // false: the image ends between the two (odd width)
+    const int x = sx0 + idx;
+    const bool edge = x < g.rh || x + 1 >= g.w - g.rh;  // has mirrored copies in the halo columns
+    // vertical prefix sums of the coefficients down the rows of this segment (what pass B consumes)
+    f2 pv[SC][4];
+#pragma unroll
+    for (int c = 0; c < SC; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pv[c][k] = 0ull;
+
     // the per-pixel solve of one output row from its prefixes P (and, in SRC_ONLY mode, the statistics gs)
-    auto math_row = [&](const int y, const uint32_t *P, const float (*gs)[9]) {
-#pragma unroll(MODE == SRC_ONLY ? MAXPX : 1)
-        for (int kk = 0; kk < MAXPX; ++kk) {
-            const int idx = tid + kk * NT;
-            if (idx >= n_out) break;
-            const int i = g.rh + idx;
-            const int x = sx0 + idx;
-            const size_t row_off = (size_t)y * g.wp;
-            float mi[3], inv[6];
-            if (MODE == SRC_ONLY) {
+    auto math_row = [&](const int y, const uint32_t *P, const f2 *gs) {
+        if (!active) return;
+        const int i = g.rh + idx;
+        const size_t row_off = (size_t)y * g.wp;
+        f2 mi[3], inv[6];
+        if (MODE == SRC_ONLY) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) mi[k] = gs[MODE == SRC_ONLY ? kk : 0][k];
+            for (int k = 0; k < 3; ++k) mi[k] = gs[k];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) inv[k] = gs[MODE == SRC_ONLY ? kk : 0][3 + k];
-            } else {
-                float m[9];
+            for (int k = 0; k < 6; ++k) inv[k] = gs[3 + k];
+        } else {
+            f2 m[9];
 #pragma unroll
-                for (int q = 0; q < 9; ++q)
-                    m[q] = box_mean(P[q * NX + i + r] - P[q * NX + i - r - 1] - bias, q_is_linear(q), g.inv_area);
-                guide_inverse(m, g.eps, inv);
-                mi[0] = m[0];
-                mi[1] = m[1];
-                mi[2] = m[2];
-                if (MODE == FULL_STORE) {
+            for (int q = 0; q < 9; ++q) m[q] = box_mean2(P + q * NX, i, r, bias, q_is_linear(q), ia2);
+            guide_inverse2(m, g.eps, inv);
+            mi[0] = m[0];
+            mi[1] = m[1];
+            mi[2] = m[2];
+            if (MODE == FULL_STORE) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) GS[k * plane + row_off + g.rh + x] = mi[k];
+                for (int k = 0; k < 3; ++k) st_pair(GS + k * plane + row_off + g.rh + x, mi[k], both);
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) GS[(3 + k) * plane + row_off + g.rh + x] = inv[k];
-                }
+                for (int k = 0; k < 6; ++k) st_pair(GS + (3 + k) * plane + row_off + g.rh + x, inv[k], both);
             }
-            // mirrored copies for the halo columns pass B will read (BORDER_REFLECT: -1-j <-> j)
-            const int xl = x < g.rh ? g.rh - 1 - x : -1;                   // padded column of the left mirror
-            const int xr = x >= g.w - g.rh ? g.rh + 2 * g.w - 1 - x : -1;  // padded column of the right mirror
+        }
 #pragma unroll
-            for (int c = 0; c < SC; ++c) {
-                float ms[4], v[4];
+        for (int c = 0; c < SC; ++c) {
+            f2 ms[4], v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int q = 9 + 4 * c + k;
-                    ms[k] = box_mean(P[(q - QB) * NX + i + r] - P[(q - QB) * NX + i - r - 1] - bias, k == 0, g.inv_area);
-                }
-                solve_source(ms, mi, inv, v);
-                float *o = g.ab + ((size_t)(img * SC + c) * 4) * plane + row_off;
+            for (int k = 0; k < 4; ++k) {
+                const int q = 9 + 4 * c + k;
+                ms[k] = box_mean2(P + (q - QB) * NX, i, r, bias, k == 0, ia2);
+            }
+            solve_source2(ms, mi, inv, v);
+            float *o = g.ab + ((size_t)(img * SC + c) * 4) * plane + row_off;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    o[k * plane + g.rh + x] = v[k];
-                    if (xl >= 0) o[k * plane + xl] = v[k];
-                    if (xr >= 0 && xr < g.wp) o[k * plane + xr] = v[k];
+            for (int k = 0; k < 4; ++k) {
+                pv[c][k] = add2(pv[c][k], v[k]);
+                st_pair(o + k * plane + g.rh + x, pv[c][k], both);
+            }
+            if (edge) {
+                // mirrored copies for the halo columns pass B will read (BORDER_REFLECT: -1-j <-> j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int xe = x + e;
+                    if (e == 1 && !both) break;
+                    const int xl = xe < g.rh ? g.rh - 1 - xe : -1;                    // padded column of the left mirror
+                    const int xr = xe >= g.w - g.rh ? g.rh + 2 * g.w - 1 - xe : -1;  // padded column of the right mirror
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float lo, hi;
+                        unpack2(pv[c][k], lo, hi);
+                        const float val = e == 0 ? lo : hi;
+                        if (xl >= 0) o[k * plane + xl] = val;
+                        if (xr >= 0 && xr < g.wp) o[k * plane + xr] = val;
+                    }
                 }
             }
         }
     };
-    auto load_stats = [&](const int y, float (*gs)[9]) {
-        const size_t row_off = (size_t)y * g.wp + g.rh + sx0;
+    auto load_stats = [&](const int y, f2 *gs) {
+        if (!active) return;
+        const float *p = GS + (size_t)y * g.wp + g.rh + x;
 #pragma unroll
-        for (int k = 0; k < MAXPX; ++k) {
-            const int idx = min(tid + k * NT, n_out - 1);
-#pragma unroll
-            for (int j = 0; j < 9; ++j) gs[k][j] = __ldg(GS + j * plane + row_off + idx);
-        }
+        for (int j = 0; j < 9; ++j) gs[j] = __ldg(reinterpret_cast<const f2 *>(p + j * plane));
     };
 
     // One loop over the rows entering the window: steps 0..2r-1 only warm the vertical sums up, every later
@@ -450,7 +606,7 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
     RowRaw<SC, C> cur_in = prefetch_row<SC, C>(PK, plane, g.wp, reflect(y0 - r, g.h), xp0c);
     RowRaw<SC, C> cur_out = cur_in;
     const int n_steps = 2 * r + (y1 - y0);
-    float gs[MODE == SRC_ONLY ? MAXPX : 1][9];
+    f2 gs[MODE == SRC_ONLY ? 9 : 1];
     for (int t = 0; t < n_steps; ++t) {
         const RowRaw<SC, C> nxt_in = prefetch_row<SC, C>(PK, plane, g.wp, reflect(y0 - r + t + 1, g.h), xp0c);
         // cached guide statistics of the pixels this thread solves in this step (row y-1): requested before
@@ -484,174 +640,234 @@ __global__ void __launch_bounds__(32 * n_groups<SC>()) pass_a_kernel(const Args 
 }
 
 // ---- pass B ---------------------------------------------------------------------------------------
-// one warp per coefficient plane (4 * SC warps); FP32 vertical sliding sums and FP32 prefixes
-template <int SC, int C>
-__global__ void __launch_bounds__(32 * 4 * SC) pass_b_kernel(const Args g)
+// One warp per (output row, coefficient plane), RB rows per CTA.  No state is carried from row to row.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    constexpr int Q = 4 * SC, NX = 32 * C, NT = 32 * Q, NP = SC == 1 ? 1 : 2;
-    extern __shared__ __align__(16) float fbuf[];  // [2][Q][NX]
-    const int tid = threadIdx.x, lane = tid & 31, pl = tid >> 5;
+    uint32_t done = 0;
+    while (!done)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+}
+
+template <int SC, int RB>
+__host__ __device__ constexpr int pass_b_warps() { return 4 * SC * RB; }
+
+template <int SC, int C, int RB>
+__global__ void __launch_bounds__(32 * pass_b_warps<SC, RB>(), SC == 1 ? 2 : 1)
+    pass_b_kernel(const __grid_constant__ CUtensorMap tmap, const Args g)
+{
+    constexpr int Q = 4 * SC, NX = 32 * C, NW = Q * RB, NP = SC == 1 ? 1 : 2;
+    constexpr uint32_t ROW_BYTES = NX * 4;  // one term: the warp's row chunk of one prefix plane
+    extern __shared__ __align__(128) float slots[];  // [NW][2][NX], then NW * 2 mbarriers
+    uint64_t *bars = reinterpret_cast<uint64_t *>(slots + NW * 2 * NX);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pl = warp % Q, rr = warp / Q;
     const int img = blockIdx.z;
-    const int sx0 = blockIdx.x * g.twe;
-    const int y0 = blockIdx.y * g.seg_rows;
-    const int y1 = min(g.h, y0 + g.seg_rows);
-    const int xp0c = min(sx0 + lane * C, g.wp - C);
+    const int sx0 = blockIdx.y * g.twe_b;
+    const int y = blockIdx.x * RB + rr;
     const size_t plane = (size_t)g.h * g.wp;
     const size_t img_px = (size_t)g.h * g.w;
-    const float *A = g.ab + ((size_t)img * Q + pl) * plane;
-    const uint32_t *PK = g.packed + (size_t)img * NP * plane;
     const int r = g.r;
-    const int n_out = min(g.twe, g.w - sx0);
+    float *slot0 = slots + (warp * 2) * NX;
 
-    float V[C];
+    if (y < g.h) {
+        const uint32_t bar0 = smem_u32(bars + warp * 2);
+        const int *pr = g.plan + (size_t)y * PLAN_STRIDE;
+        const int cnt = pr[0];
+        // lane 0 owns this warp's two barriers and issues its TMA loads: box = half a row chunk (NX/4 8-byte
+        // elements), two boxes per term
+        auto issue = [&](int t) {
+            const int s = t & 1;
+            const uint32_t bar = bar0 + 8 * s;
+            const uint32_t dst = smem_u32(slot0 + s * NX);
+            const int row = pr[4 + t];
+            const int c0 = sx0 / 2, c2 = img * Q + pl;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ROW_BYTES) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dst), "l"(&tmap), "r"(c0), "r"(row), "r"(c2), "r"(bar)
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dst + ROW_BYTES / 2), "l"(&tmap), "r"(c0 + NX / 4), "r"(row), "r"(c2), "r"(bar)
+                : "memory");
+        };
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            issue(0);
+            if (cnt > 1) issue(1);
+        }
+        __syncwarp();
+        float acc[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) V[c] = 0.0f;
-    struct Chunk {
-        float v[C];
-    };
-    auto fetch = [&](int yy) {
-        Chunk k;
-        const float4 *p = reinterpret_cast<const float4 *>(A + (size_t)yy * g.wp + xp0c);
+        for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+        for (int t = 0; t < cnt; ++t) {
+            const int s = t & 1;
+            const float wgt = __int_as_float(pr[4 + MAXT + t]);
+            mbar_wait(bar0 + 8 * s, (uint32_t)(t >> 1) & 1u);
+            const float4 *sp = reinterpret_cast<const float4 *>(slot0 + s * NX + lane * C);
+            const f2 w2 = dup2(wgt);
+#pragma unroll
+            for (int c = 0; c < C; c += 4) {
+                const float4 v = sp[c / 4];
+                f2 a01 = pack2(acc[c], acc[c + 1]), a23 = pack2(acc[c + 2], acc[c + 3]);
+                ffma2(a01, w2, pack2(v.x, v.y));  // weights are +-1 (+-2): exact products
+                ffma2(a23, w2, pack2(v.z, v.w));
+                unpack2(a01, acc[c], acc[c + 1]);
+                unpack2(a23, acc[c + 2], acc[c + 3]);
+            }
+            __syncwarp();  // every lane has read the slot before lane 0 lets the next term overwrite it
+            if (lane == 0 && t + 2 < cnt) issue(t + 2);
+        }
+        // horizontal prefix over the strip: serial over the lane's C columns, then one warp scan of the lane totals
+        float run = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            run += acc[c];
+            acc[c] = run;
+        }
+        float incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float tt = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += tt;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.0f;
+        // the prefixes replace the first slot (all of this warp's loads have landed and been consumed)
+        float4 *dp = reinterpret_cast<float4 *>(slot0 + lane * C);
+        const f2 e2 = dup2(excl);
 #pragma unroll
         for (int c = 0; c < C; c += 4) {
-            const float4 t = __ldg(p + c / 4);
-            k.v[c] = t.x;
-            k.v[c + 1] = t.y;
-            k.v[c + 2] = t.z;
-            k.v[c + 3] = t.w;
+            float p0, p1, p2, p3;
+            unpack2(add2(pack2(acc[c], acc[c + 1]), e2), p0, p1);
+            unpack2(add2(pack2(acc[c + 2], acc[c + 3]), e2), p2, p3);
+            dp[c / 4] = make_float4(p0, p1, p2, p3);
         }
-        return k;
-    };
-    auto add = [&](const Chunk &k, float sign) {  // exact either way: sign * x is x or -x
-#pragma unroll
-        for (int c = 0; c < C; c += 2) {
-            unsigned long long v = pack2(V[c], V[c + 1]);
-            ffma2(v, pack2(sign, sign), pack2(k.v[c], k.v[c + 1]));
-            unpack2(v, V[c], V[c + 1]);
-        }
-    };
-    // Rows are loaded into registers PF steps ahead of their use.  Measured on B200 (64 x 512 x 384, r = 45):
-    // PF = 3 costs occupancy (128 registers) and is 35 % slower; an additional prefetch.global.L2 eight rows
-    // ahead is 15 % slower (the kernel already moves 3.4x the compulsory bytes: the leaving-row stream and the
-    // strip overlap are re-read from DRAM, so extra requests only add pressure).
-    constexpr int PF = 1;
-    Chunk qin[PF], qout[PF];
-#pragma unroll
-    for (int i = 0; i < PF; ++i) qin[i] = qout[i] = fetch(reflect(y0 - r + i, g.h));
-    // output row y from the prefixes P of the four (twelve) coefficient planes
-    auto math_row = [&](const int y, const float *P) {
-        for (int idx = tid; idx < n_out; idx += NT) {
-            const int i = g.rh + idx;
-            const int x = sx0 + idx;
-            const uint32_t gw = PK[(size_t)y * g.wp + g.rh + x];
-            const float i0 = b2f(gw, 0), i1 = b2f(gw, 1), i2 = b2f(gw, 2);
-            uint8_t res[SC];
-#pragma unroll
-            for (int c = 0; c < SC; ++c) {
-                float m[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float *Pq = P + (4 * c + k) * NX;
-                    m[k] = __fmul_rn(Pq[i + r] - Pq[i - r - 1], g.inv_area);
-                }
-                float v = m[3];
-                v = __fadd_rn(v, __fmul_rn(m[0], i0));
-                v = __fadd_rn(v, __fmul_rn(m[1], i1));
-                v = __fadd_rn(v, __fmul_rn(m[2], i2));
-                res[c] = sat_u8(v);
-            }
-            if (g.store_dst) {
-                uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + x) * SC;
-#pragma unroll
-                for (int c = 0; c < SC; ++c) o[c] = res[c];
-            }
-            if (g.store_packed) {
-                // the next iteration filters this output: put it where pack_kernel would have put it, mirrored
-                // halo columns included.  Other CTAs of this launch read only the guide bytes of these words.
-                const int xl = x < g.rh ? g.rh - 1 - x : -1;
-                const int xr = x >= g.w - g.rh ? g.rh + 2 * g.w - 1 - x : -1;
-                uint32_t *row = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp;
-                if (SC == 1) {
-                    uint8_t *rb = reinterpret_cast<uint8_t *>(row);
-                    rb[(size_t)(g.rh + x) * 4 + 3] = res[0];
-                    if (xl >= 0) rb[(size_t)xl * 4 + 3] = res[0];
-                    if (xr >= 0 && xr < g.wp) rb[(size_t)xr * 4 + 3] = res[0];
-                } else {
-                    const uint32_t wv = res[0] | ((uint32_t)res[1 % SC] << 8) | ((uint32_t)res[2 % SC] << 16);
-                    row[plane + g.rh + x] = wv;
-                    if (xl >= 0) row[plane + xl] = wv;
-                    if (xr >= 0 && xr < g.wp) row[plane + xr] = wv;
-                }
-            }
-        }
-    };
-    // software-pipelined by one row like pass A: between two barriers a warp scans row y and finishes row y-1
-    const int n_steps = 2 * r + (y1 - y0);
-    for (int t = 0; t < n_steps; ++t) {
-        add(qin[0], 1.0f);
-#pragma unroll
-        for (int i = 0; i + 1 < PF; ++i) qin[i] = qin[i + 1];
-        qin[PF - 1] = fetch(reflect(y0 - r + t + PF, g.h));
-        if (t < 2 * r) continue;
-        const int y = y0 + t - 2 * r;
-        float *P = fbuf + ((y - y0) & 1) * (Q * NX);
-        {
-            float pre[C];
-            float run = 0.0f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                run += V[c];
-                pre[c] = run;
-            }
-            float incl = run;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const float tt = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += tt;
-            }
-            // exclusive prefix by a shift, NOT incl - run: the chunk right of the last needed column may hold
-            // unwritten coefficients (inf/NaN garbage), and inf - inf would poison this lane's own prefix
-            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            if (lane == 0) excl = 0.0f;
-            float *dstp = P + pl * NX + lane * C;
-#pragma unroll
-            for (int c = 0; c < C; c += 4)
-                *reinterpret_cast<float4 *>(dstp + c) =
-                    make_float4(pre[c] + excl, pre[c + 1] + excl, pre[c + 2] + excl, pre[c + 3] + excl);
-        }
-        add(qout[0], -1.0f);
-#pragma unroll
-        for (int i = 0; i + 1 < PF; ++i) qout[i] = qout[i + 1];
-        qout[PF - 1] = fetch(reflect(y - r + PF, g.h));
-        if (y > y0) math_row(y - 1, fbuf + ((y - 1 - y0) & 1) * (Q * NX));
-        __syncthreads();
     }
-    math_row(y1 - 1, fbuf + ((y1 - 1 - y0) & 1) * (Q * NX));
+    __syncthreads();
+    if (y >= g.h) return;
+
+    // the Q warps of a row share its pixels: one pixel pair per thread and step
+    const float *Prow = slots + (rr * Q * 2) * NX;  // plane k of this row: Prow + k * 2 * NX
+    const uint32_t *PK = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp;
+    const int n_out = min(g.twe_b, g.w - sx0);
+    const f2 ia2 = dup2(g.inv_area);
+    const bool w_even = (g.w & 1) == 0;
+    for (int idx = 2 * (pl * 32 + lane); idx < n_out; idx += 2 * 32 * Q) {
+        const bool both = idx + 1 < n_out;
+        const int i = g.rh + idx;
+        const int x = sx0 + idx;
+        const uint2 gw = *reinterpret_cast<const uint2 *>(PK + g.rh + x);
+        const f2 i0 = b2f2(gw.x, gw.y, 0, false), i1 = b2f2(gw.x, gw.y, 1, false), i2 = b2f2(gw.x, gw.y, 2, false);
+        uint32_t res0[SC], res1[SC];
+#pragma unroll
+        for (int c = 0; c < SC; ++c) {
+            f2 m[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float *Pq = Prow + (4 * c + k) * 2 * NX;
+                m[k] = mul2(sub2(pack2(Pq[i + r], Pq[i + r + 1]), pack2(Pq[i - r - 1], Pq[i - r])), ia2);
+            }
+            f2 v = m[3];
+            v = add2(v, mul2(m[0], i0));
+            v = add2(v, mul2(m[1], i1));
+            v = add2(v, mul2(m[2], i2));
+            float v0, v1;
+            unpack2(v, v0, v1);
+            res0[c] = sat_u8(v0);
+            res1[c] = sat_u8(v1);
+        }
+        if (g.store_dst) {
+            uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + x) * SC;
+            if (SC == 1) {
+                if (both && w_even)
+                    *reinterpret_cast<uint16_t *>(o) = (uint16_t)(res0[0] | (res1[0] << 8));
+                else {
+                    o[0] = (uint8_t)res0[0];
+                    if (both) o[1] = (uint8_t)res1[0];
+                }
+            } else {
+                if (both && w_even) {
+                    uint16_t *o2 = reinterpret_cast<uint16_t *>(o);
+                    o2[0] = (uint16_t)(res0[0] | (res0[1 % SC] << 8));
+                    o2[1] = (uint16_t)(res0[2 % SC] | (res1[0] << 8));
+                    o2[2] = (uint16_t)(res1[1 % SC] | (res1[2 % SC] << 8));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < SC; ++c) o[c] = (uint8_t)res0[c];
+                    if (both)
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) o[SC + c] = (uint8_t)res1[c];
+                }
+            }
+        }
+        if (g.store_packed) {
+            // the next iteration filters this output: put it where pack_kernel would have put it, mirrored
+            // halo columns included.  Other CTAs of this launch read only the guide bytes of these words.
+            uint32_t *row = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp + (SC == 1 ? 0 : plane);
+            const uint32_t w0 = SC == 1 ? (gw.x & 0x00FFFFFFu) | (res0[0] << 24)
+                                        : res0[0] | (res0[1 % SC] << 8) | (res0[2 % SC] << 16);
+            const uint32_t w1 = SC == 1 ? (gw.y & 0x00FFFFFFu) | (res1[0] << 24)
+                                        : res1[0] | (res1[1 % SC] << 8) | (res1[2 % SC] << 16);
+            if (both)
+                *reinterpret_cast<uint2 *>(row + g.rh + x) = make_uint2(w0, w1);
+            else
+                row[g.rh + x] = w0;
+            if (x < g.rh || x + 1 >= g.w - g.rh) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (e == 1 && !both) break;
+                    const int xe = x + e;
+                    const uint32_t wv = e == 0 ? w0 : w1;
+                    const int xl = xe < g.rh ? g.rh - 1 - xe : -1;
+                    const int xr = xe >= g.w - g.rh ? g.rh + 2 * g.w - 1 - xe : -1;
+                    if (xl >= 0) row[xl] = wv;
+                    if (xr >= 0 && xr < g.wp) row[xr] = wv;
+                }
+            }
+        }
+    }
 }
 
 // ---- host -------------------------------------------------------------------------------------------
 struct Plan {
-    int C, strips, twe, rh, wp, segs, seg_rows;
+    int C, strips, twe;        // pass A strips
+    int CB, strips_b, twe_b;   // pass B strips
+    int rh, wp;
 };
 
 static int halo(int r) { return (r + 1 + 3) & ~3; }
 // + 16: the chunk (<= 16 columns) that holds the right-most needed column must lie inside the row
 static int pitch(int w, int r) { return (w + 2 * halo(r) + 16 + 3) & ~3; }
 
-// tuning overrides (development only): RF_GF2_SEGS_A / RF_GF2_SEGS_B force the number of row segments
+// tuning override (development only): RF_GF2_SEGS_A forces the number of row segments of pass A
 static int env_int(const char *name)
 {
     const char *e = getenv(name);
     return e ? atoi(e) : 0;
 }
 
-static Plan make_plan(int h, int w, int r)
+static Plan make_plan(int sc, int h, int w, int r)
 {
     Plan best{};
-    long best_cost = -1;
     const int rh = halo(r);
-    for (int C : {8, 12, 16}) {
-        const int tw = 32 * C - 2 * rh;
+    best.rh = rh;
+    best.wp = pitch(w, r);
+    long best_cost = -1;
+    const int max_pairs = 32 * (sc == 1 ? 4 : 6);  // pass A solves one pixel pair per thread and row
+    for (int C : {8, 12}) {  // wider chunks never pay: a strip emits at most 2 * threads columns
+        int tw = 32 * C - 2 * rh;
+        if (tw > 2 * max_pairs) tw = 2 * max_pairs;
         if (tw < 32) continue;
         const int strips = (w + tw - 1) / tw;
         int twe = ((w + strips - 1) / strips + 3) & ~3;
@@ -659,35 +875,130 @@ static Plan make_plan(int h, int w, int r)
         const long cost = (long)strips * 32 * C;  // columns touched per image row
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
-            best = Plan{C, strips, twe, rh, pitch(w, r), 1, h};
+            best.C = C;
+            best.strips = strips;
+            best.twe = twe;
+        }
+    }
+    best_cost = -1;
+    for (int C : {12, 20}) {  // 48- and 80-byte lane chunks: conflict-free 128-bit shared-memory accesses
+        const int tw = 32 * C - 2 * rh;
+        if (tw < 32) continue;
+        const int strips = (w + tw - 1) / tw;
+        int twe = ((w + strips - 1) / strips + 3) & ~3;
+        if (twe > tw) twe = tw & ~3;
+        const long cost = (long)strips * 32 * C;
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best.CB = C;
+            best.strips_b = strips;
+            best.twe_b = twe;
         }
     }
     return best;
 }
 
+// does every row's window fit into MAXT prefix rows for this segmentation?  (always for h > r and segments of at
+// least 64 rows; checked because the segment count depends on the batch size)
+static bool plan_fits(int h, int r, int seg_rows)
+{
+    static std::mutex mu;
+    static int last[4] = {0, 0, 0, 0};  // h, r, seg_rows, result
+    std::lock_guard<std::mutex> lock(mu);
+    if (last[0] == h && last[1] == r && last[2] == seg_rows) return last[3] != 0;
+    bool ok = true;
+    RowTerms t;
+    for (int y = 0; y < h && ok; ++y) {
+        row_terms(t, y, h, r, seg_rows);
+        ok = t.cnt <= MAXT;
+    }
+    last[0] = h;
+    last[1] = r;
+    last[2] = seg_rows;
+    last[3] = ok ? 1 : 0;
+    return ok;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (PFN_cuTensorMapEncodeTiled)f;
+    }();
+    return fn;
+}
+
+// 3-D map of the prefix planes as 8-byte elements: (wp / 2, h, planes); box = half a lane-chunk row (nx / 4 elements)
+static int make_tensor_map(CUtensorMap *tm, float *base, int wp, int h, size_t planes, int nx)
+{
+    PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return fail(RF_ECUDA, "gf2: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)wp / 2, (cuuint64_t)h, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)wp * 4, (cuuint64_t)h * wp * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)nx / 4, 1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(RF_ECUDA, "gf2: cuTensorMapEncodeTiled failed (CUresult %d)", (int)rc);
+    return RF_OK;
+}
+
+// one-time per-device kernel attributes; safe from several host threads
+struct DeviceOnce {
+    std::mutex mu;
+    bool done[64] = {};
+};
+
+template <int SC, int CB>
+static int launch_b(const Args &a, const Plan &p, cudaStream_t st)
+{
+    constexpr int RB = SC == 1 ? 4 : 1, NW = pass_b_warps<SC, RB>(), NX = 32 * CB;
+    constexpr size_t smem = (size_t)NW * 2 * NX * sizeof(float) + (size_t)NW * 2 * sizeof(uint64_t);
+    static DeviceOnce once;
+    int dev = 0;
+    RF_CUDA_TRY(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(once.mu);
+        if (!once.done[dev & 63]) {
+            RF_CUDA_TRY(cudaFuncSetAttribute(pass_b_kernel<SC, CB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            once.done[dev & 63] = true;
+        }
+    }
+    CUtensorMap tm;
+    const int rc = make_tensor_map(&tm, a.ab, a.wp, a.h, (size_t)a.n * 4 * SC, NX);
+    if (rc != RF_OK) return rc;
+    const dim3 grid((a.h + RB - 1) / RB, p.strips_b, a.n);
+    pass_b_kernel<SC, CB, RB><<<grid, 32 * NW, smem, st>>>(tm, a);
+    RF_LAUNCH_CHECK("gf2::pass_b_kernel");
+    return RF_OK;
+}
+
 template <int SC, int C>
 static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
 {
-    constexpr int QA_ = 9 + 4 * SC, QS_ = 4 * SC, QB_ = 4 * SC, NX = 32 * C, NTA = 32 * n_groups<SC>();
+    constexpr int QA_ = 9 + 4 * SC, QS_ = 4 * SC, NX = 32 * C, NTA = 32 * n_groups<SC>();
     const size_t smem_a = (size_t)2 * QA_ * NX * sizeof(uint32_t);
     const size_t smem_s = (size_t)2 * QS_ * NX * sizeof(uint32_t);
-    const size_t smem_b = (size_t)2 * QB_ * NX * sizeof(float);
-    static bool configured[64] = {};
-    static int occ_a = 1, occ_s = 1, occ_b = 1;
+    static DeviceOnce once;
+    static int occ_a = 1;
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C, FULL_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C, SRC_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        RF_CUDA_TRY(cudaFuncSetAttribute(pass_b_kernel<SC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        RF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, pass_a_kernel<SC, C, FULL_STORE>, NTA, smem_a));
-        RF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, pass_a_kernel<SC, C, SRC_ONLY>, NTA, smem_s));
-        RF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, pass_b_kernel<SC, C>, 32 * 4 * SC, smem_b));
-        if (occ_a < 1) occ_a = 1;
-        if (occ_s < 1) occ_s = 1;
-        if (occ_b < 1) occ_b = 1;
-        configured[dev & 63] = true;
+    {
+        std::lock_guard<std::mutex> lock(once.mu);
+        if (!once.done[dev & 63]) {
+            RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C, FULL_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C, SRC_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            RF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, pass_a_kernel<SC, C, FULL_STORE>, NTA, smem_a));
+            if (occ_a < 1) occ_a = 1;
+            once.done[dev & 63] = true;
+        }
     }
     dim3 pgrid((a.wp + 255) / 256, (a.h + PACK_ROWS - 1) / PACK_ROWS, a.n);
     pack_kernel<SC><<<pgrid, 256, 0, st>>>(a);
@@ -695,41 +1006,38 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
     // Row segments: the vertical sums make a column strictly sequential, so small batches are split into
     // row segments (each pays 2r warm-up rows) until the grid fills ONE wave of resident CTAs -- measured:
     // more than one wave loses to tail effects, fewer leaves SMs idle (profiles/r01_gf2_segments.txt).
-    static const int force_a = env_int("RF_GF2_SEGS_A"), force_b = env_int("RF_GF2_SEGS_B");
+    // One segmentation for every iteration: the prefix rows pass A writes restart at segment boundaries, and the
+    // row plan of pass B is built for exactly that segmentation.
+    static const int force_a = env_int("RF_GF2_SEGS_A");
     const long ctas = (long)p.strips * a.n;
-    // shortest segment: 64 rows for pass A, 48 for pass B, whose warm-up rows are cheap (measured at 64 x 512x384:
-    // 6 segments 1.50 ms for three iterations, 8 segments 1.45 ms, 10 segments 1.67 ms)
-    auto pick = [&](int occ, int forced, int min_rows) {
-        if (forced > 0) return forced;
-        const int max_segs = a.h / min_rows > 1 ? a.h / min_rows : 1;
-        long s = (long)sm_count() * occ / ctas;
+    int segs = force_a;
+    if (segs <= 0) {
+        const int max_segs = a.h / 64 > 1 ? a.h / 64 : 1;  // shortest segment: 64 rows
+        long s = (long)sm_count() * occ_a / ctas;
         if (s < 1) s = 1;
         if (s > max_segs) s = max_segs;
-        return (int)s;
-    };
-    const int sa = pick(occ_a, force_a, 64), ss = pick(occ_s, force_a, 64), sb = pick(occ_b, force_b, 48);
-    auto grid_for = [&](int segs) {
-        a.seg_rows = (a.h + segs - 1) / segs;
-        return dim3(p.strips, (a.h + a.seg_rows - 1) / a.seg_rows, a.n);
-    };
+        segs = (int)s;
+    }
+    a.seg_rows = (a.h + segs - 1) / segs;
+    if (!plan_fits(a.h, a.r, a.seg_rows)) a.seg_rows = a.h;  // one segment: at most two terms per reflected copy
+    const dim3 grid_a(p.strips, (a.h + a.seg_rows - 1) / a.seg_rows, a.n);
+    plan_kernel<<<(a.h + 127) / 128, 128, 0, st>>>(const_cast<int *>(a.plan), a.h, a.r, a.seg_rows);
+    RF_LAUNCH_CHECK("gf2::plan_kernel");
     for (int it = 0; it < iterations; ++it) {
         const bool last = it == iterations - 1;
         if (it == 0) {
-            const dim3 grid = grid_for(sa);
             if (iterations > 1)
-                pass_a_kernel<SC, C, FULL_STORE><<<grid, NTA, smem_a, st>>>(a);
+                pass_a_kernel<SC, C, FULL_STORE><<<grid_a, NTA, smem_a, st>>>(a);
             else
-                pass_a_kernel<SC, C, FULL><<<grid, NTA, smem_a, st>>>(a);
+                pass_a_kernel<SC, C, FULL><<<grid_a, NTA, smem_a, st>>>(a);
         } else {
-            const dim3 grid = grid_for(ss);
-            pass_a_kernel<SC, C, SRC_ONLY><<<grid, NTA, smem_s, st>>>(a);
+            pass_a_kernel<SC, C, SRC_ONLY><<<grid_a, NTA, smem_s, st>>>(a);
         }
         RF_LAUNCH_CHECK("gf2::pass_a_kernel");
         a.store_dst = last ? 1 : 0;
         a.store_packed = last ? 0 : 1;
-        const dim3 grid = grid_for(sb);
-        pass_b_kernel<SC, C><<<grid, 32 * 4 * SC, smem_b, st>>>(a);
-        RF_LAUNCH_CHECK("gf2::pass_b_kernel");
+        const int rc = p.CB == 12 ? launch_b<SC, 12>(a, p, st) : launch_b<SC, 20>(a, p, st);
+        if (rc != RF_OK) return rc;
     }
     return RF_OK;
 }
@@ -740,13 +1048,16 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
 // guides, r = 1, eps <= 0.05: 0.5 % of bytes move by 1 LSB and single bytes by 2; the generic path is bit-equal to
 // the oracle there).  From r = 8 up the deviation is below 1e-3 of the bytes, +-1 LSB.
 constexpr int MIN_RADIUS = 8;
-bool supported(int r, int h, int w) { return r >= MIN_RADIUS && r <= MAX_RADIUS && w >= halo(r) && h <= 65535; }
+bool supported(int r, int h, int w) { return r >= MIN_RADIUS && r <= MAX_RADIUS && w >= halo(r) && h > r && h <= 65535; }
 
-// packed planes + coefficient planes (+ nine guide-statistics planes when the filter is iterated)
+static size_t plan_bytes(int h) { return ((size_t)h * PLAN_STRIDE * sizeof(int) + 15) & ~(size_t)15; }
+
+// packed planes + prefix planes (+ nine guide-statistics planes when the filter is iterated) + the row plan (needed
+// once per call; counted per image so that any chunk of the batch has room for it)
 size_t workspace_per_image(int sc, int h, int w, int r, int iterations)
 {
     const size_t plane = (size_t)h * pitch(w, r);
-    return plane * 4 * (sc == 1 ? 1 : 2) + plane * 4 * 4 * sc + (iterations > 1 ? plane * 4 * 9 : 0);
+    return plane * 4 * (sc == 1 ? 1 : 2) + plane * 4 * 4 * sc + (iterations > 1 ? plane * 4 * 9 : 0) + plan_bytes(h);
 }
 
 int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws, int n, int h, int w, int r,
@@ -763,22 +1074,23 @@ int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws
     a.eps = (float)eps;
     const int k = 2 * r + 1;
     a.inv_area = (float)(1.0 / ((double)k * k));
-    const Plan p = make_plan(h, w, r);
+    const Plan p = make_plan(sc, h, w, r);
     a.rh = p.rh;
     a.wp = p.wp;
     a.twe = p.twe;
-    a.seg_rows = p.seg_rows;
+    a.twe_b = p.twe_b;
+    a.seg_rows = h;
     a.store_dst = 1;
     a.store_packed = 0;
     const size_t plane = (size_t)h * p.wp;
     a.packed = (uint32_t *)ws;
     a.ab = (float *)((uint32_t *)ws + (size_t)n * (sc == 1 ? 1 : 2) * plane);
     a.gstat = iterations > 1 ? a.ab + (size_t)n * sc * 4 * plane : nullptr;
+    a.plan = (const int *)(a.ab + (size_t)n * sc * 4 * plane + (iterations > 1 ? (size_t)n * 9 * plane : 0));
 #define RF_GF2_LAUNCH(SC_)                                            \
     switch (p.C) {                                                    \
         case 8: return launch<SC_, 8>(a, p, iterations, st);          \
-        case 12: return launch<SC_, 12>(a, p, iterations, st);        \
-        default: return launch<SC_, 16>(a, p, iterations, st);        \
+        default: return launch<SC_, 12>(a, p, iterations, st);        \
     }
     if (sc == 1) { RF_GF2_LAUNCH(1) }
     RF_GF2_LAUNCH(3)
@@ -787,3 +1099,17 @@ int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws
 
 }  // namespace gf2
 }  // namespace rf
+
+// row plan of pass B for one output row (diagnostic entry point: lets the CPU-side tests check the window
+// decomposition against a brute-force sum).  Returns the number of terms (> 12 = does not fit).
+extern "C" int rf_guided_row_terms(int h, int radius, int seg_rows, int y, int *rows, float *weights)
+{
+    if (h < 1 || radius < 0 || seg_rows < 1 || y < 0 || y >= h || !rows || !weights) return -1;
+    rf::gf2::RowTerms t;
+    rf::gf2::row_terms(t, y, h, radius, seg_rows);
+    for (int i = 0; i < t.cnt && i < rf::gf2::MAXT; ++i) {
+        rows[i] = t.row[i];
+        weights[i] = t.wgt[i];
+    }
+    return t.cnt;
+}

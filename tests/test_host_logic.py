@@ -190,6 +190,32 @@ def test_geometry_helper_matches_survey():
     assert L.rf_joint_bilateral_geometry(22.0, 9, ctypes.byref(r), ctypes.byref(t)) == 0 and r.value == 4
 
 
+def test_guided_row_plan_equals_brute_force_window_sums():
+    """Pass B of the guided filter sums a few rows of segment-restarted vertical prefix sums instead of sliding a
+    window (csrc/gf2.cu row_terms): check the decomposition against the BORDER_REFLECT window sum it stands for."""
+    L = _native.lib()
+    rows, wgts = (ctypes.c_int * 12)(), (ctypes.c_float * 12)()
+    rng = np.random.default_rng(5)
+    worst = 0
+    for h, r, seg in [(384, 45, 96), (384, 45, 64), (384, 45, 384), (2160, 45, 64), (100, 64, 100), (65, 64, 64),
+                      (97, 45, 65), (50, 8, 50), (200, 33, 67), (46, 45, 46), (130, 64, 65), (9, 8, 9)]:
+        v = rng.integers(0, 1000, h).astype(np.int64)
+        pv = np.zeros(h, np.int64)                       # prefix sums restarted every `seg` rows, as pass A stores them
+        for y in range(h):
+            pv[y] = v[y] + (pv[y - 1] if y % seg else 0)
+        idx = np.arange(-r, h + r)
+        refl = np.where(idx < 0, -idx - 1, np.where(idx >= h, 2 * h - 1 - idx, idx))   # fedcba|abcdefgh|hgfedcb
+        assert refl.min() >= 0 and refl.max() < h        # single reflection: h > r
+        for y in range(h):
+            n = L.rf_guided_row_terms(h, r, seg, y, rows, wgts)
+            assert 1 <= n <= 12, (h, r, seg, y, n)
+            worst = max(worst, n)
+            got = sum(int(wgts[i]) * int(pv[rows[i]]) for i in range(n))
+            assert got == int(v[refl[y:y + 2 * r + 1]].sum()), (h, r, seg, y)
+    assert worst <= 12
+    assert L.rf_guided_row_terms(10, 3, 0, 0, rows, wgts) == -1
+
+
 def test_argument_errors_do_not_need_a_gpu():
     L = _native.lib()
     assert L.rf_joint_bilateral_u8(None, 3, None, 3, None, 1, 4, 4, 20.0, 22.0, -1, 0, None) == _native.RF_EINVAL
