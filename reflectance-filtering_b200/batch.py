@@ -111,7 +111,9 @@ def run_batch(files: Sequence[str], path_out: str, mode: str = "decompose+filter
     pinned: Dict[tuple, torch.Tensor] = {}
 
     def pin(tag, shape, slot):
-        # at most two groups are in flight, so three rotating buffers per (tag, shape) are never shared
+        # At most two groups are in flight on the GPU, so three rotating buffers per (tag, shape) are never shared
+        # by two groups' copies.  The ENCODERS read the output buffers later, on the save pool: process_group
+        # waits for the saves of the group that used these buffers last (slot_saves) before it overwrites them.
         key = (tag, tuple(shape), slot % 3)
         buf = pinned.get(key)
         if buf is None:
@@ -119,6 +121,7 @@ def run_batch(files: Sequence[str], path_out: str, mode: str = "decompose+filter
         return buf
 
     pending_writes = []
+    slot_saves: Dict[int, list] = {}  # slot % 3 -> save futures that still read that slot's pinned output buffers
     todo = []
     for f in files:
         r_name, f_name = out_names(f)
@@ -185,29 +188,54 @@ def run_batch(files: Sequence[str], path_out: str, mode: str = "decompose+filter
                         guide = filters.replicate_gray_device(cur) if gray else cur  # the image guides itself
                         cur = filters.guided_device(guide, cur, int(sigma_spatial), sigma_color)
                 outs["f"] = filters.replicate_gray_device(cur) if gray else cur  # what cv2.imwrite gets
+            for fut in slot_saves.pop(slot % 3, []):  # encoders of the group three slots back: done reading?
+                fut.result()
             host_out = {k: pin("out_" + k, v.shape, slot) for k, v in outs.items()}
             for k, v in outs.items():
                 host_out[k].copy_(v, non_blocking=True)
-        return s, items, host_out
+        return s, items, host_out, slot
 
     def flush(job, pool):
-        s, items, host_out = job
+        s, items, host_out, slot = job
         s.synchronize()
+        mine = slot_saves.setdefault(slot % 3, [])
+
+        def submit(path, view):
+            fut = pool.submit(save, path, view)
+            pending_writes.append(fut)
+            mine.append(fut)
+
         for i, (f, img, _) in enumerate(items):
             r_name, f_name = out_names(f)
             if "r" in host_out:
-                pending_writes.append(pool.submit(save, r_name, host_out["r"][i].numpy()))
+                submit(r_name, host_out["r"][i].numpy())
             for key, tail in (("rc", "-r_colorized.png"), ("sc", "-s_colorized.png")):
                 if key in host_out:
-                    pending_writes.append(pool.submit(save, os.path.join(path_out, _stem(f) + tail),
-                                                      host_out[key][i].numpy()))
+                    submit(os.path.join(path_out, _stem(f) + tail), host_out[key][i].numpy())
             if "f" in host_out:
-                pending_writes.append(pool.submit(save, f_name, host_out["f"][i].numpy()))
+                submit(f_name, host_out["f"][i].numpy())
             res["images"] += 1
             res["pixels"] += img.shape[0] * img.shape[1]
 
-    with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool:
-        loaded = pool.map(load, todo)
+    def load_ahead(pool, window):
+        """Decoded files in order, with at most ``window`` decodes queued or waiting to be consumed (the whole
+        folder is never held in RAM, and the decode queue cannot starve the encoders: they have their own pool)."""
+        it = iter(todo)
+        queue = []
+        for f in it:
+            queue.append(pool.submit(load, f))
+            if len(queue) >= window:
+                break
+        while queue:
+            out = queue.pop(0).result()
+            for f in it:
+                queue.append(pool.submit(load, f))
+                break
+            yield out
+
+    n_io = max(1, io_threads)
+    with ThreadPoolExecutor(max_workers=n_io) as load_pool, ThreadPoolExecutor(max_workers=n_io) as pool:
+        loaded = load_ahead(load_pool, max(2 * chunk, 2 * n_io))
         groups: Dict[tuple, list] = {}
         in_flight = []
         slot = 0

@@ -572,6 +572,26 @@ def test_batch_front_end_matches_per_file_cli(tmp_path, net):
     assert np.array_equal(cv2.imread(str(out_a / "im2_guided_c3.0s7.0.png")), cur)
 
 
+def test_batch_front_end_many_same_shape_chunks(tmp_path, net):
+    """Seven chunks of one shape: the three rotating pinned output buffers are reused while encoders of
+    earlier chunks may still be reading them.  Every file must hold ITS image's bytes."""
+    import cv2
+    from reflectance_filtering_b200 import batch
+    src_dir, out = tmp_path / "in", tmp_path / "out"
+    src_dir.mkdir()
+    out.mkdir()
+    n, h, w = 14, 96, 128
+    imgs = [synth.natural(h, w, 900 + i) for i in range(n)]
+    for i, im in enumerate(imgs):
+        cv2.imwrite(str(src_dir / ("im%02d.png" % i)), im)
+    res = batch.run_batch(batch.list_inputs(str(src_dir)), str(out), mode="decompose", chunk=2, io_threads=2)
+    assert not res["errors"] and len(res["written"]) == n
+    want = net.forward_device(dev_u8(np.stack(imgs)), want_f32=False, want_u8=True)[1].cpu().numpy()
+    for i in range(n):
+        got = cv2.imread(str(out / ("im%02d-r.png" % i)), cv2.IMREAD_UNCHANGED)
+        assert got is not None and np.array_equal(got, want[i]), i
+
+
 def test_whdr_matches_reference_golden_and_oracle(golden_dir, net):
     """rf_whdr_f32 against the reference's own whdr() (golden_whdr.npz) and the restatement on CNN output."""
     from reflectance_filtering_b200 import whdr
