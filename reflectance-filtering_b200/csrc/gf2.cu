@@ -44,6 +44,7 @@
 #include <mutex>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -659,15 +660,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 template <int SC, int RB>
 __host__ __device__ constexpr int pass_b_warps() { return 4 * SC * RB; }
 
-template <int SC, int C, int RB>
-__global__ void __launch_bounds__(32 * pass_b_warps<SC, RB>(), SC == 1 ? 2 : 1)
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// The whole issue path of pass B is warp-uniform: the warp index, the output row and the row plan are broadcast
+// values, and the loads are issued by an elected lane.  (Issued from `if (lane == 0)` the compiler wrapped every
+// cp.async.bulk.tensor in per-operand R2UR + vote loops: 60 of the 75 instructions of the term loop,
+// profiles/r02_gf_v0_blocks.txt.)
+template <int SC, int C, int RB, int NS>
+__global__ void __launch_bounds__(32 * pass_b_warps<SC, RB>(), SC == 1 ? 8 / RB : 1)
     pass_b_kernel(const __grid_constant__ CUtensorMap tmap, const Args g)
 {
     constexpr int Q = 4 * SC, NX = 32 * C, NW = Q * RB, NP = SC == 1 ? 1 : 2;
     constexpr uint32_t ROW_BYTES = NX * 4;  // one term: the warp's row chunk of one prefix plane
-    extern __shared__ __align__(128) float slots[];  // [NW][2][NX], then NW * 2 mbarriers
-    uint64_t *bars = reinterpret_cast<uint64_t *>(slots + NW * 2 * NX);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(128) float slots[];  // [NW][NS][NX], then NW * NS mbarriers
+    uint64_t *bars = reinterpret_cast<uint64_t *>(slots + NW * NS * NX);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int pl = warp % Q, rr = warp / Q;
     const int img = blockIdx.z;
     const int sx0 = blockIdx.y * g.twe_b;
@@ -675,45 +693,47 @@ __global__ void __launch_bounds__(32 * pass_b_warps<SC, RB>(), SC == 1 ? 2 : 1)
     const size_t plane = (size_t)g.h * g.wp;
     const size_t img_px = (size_t)g.h * g.w;
     const int r = g.r;
-    float *slot0 = slots + (warp * 2) * NX;
+    float *slot0 = slots + (warp * NS) * NX;
 
     if (y < g.h) {
-        const uint32_t bar0 = smem_u32(bars + warp * 2);
-        const int *pr = g.plan + (size_t)y * PLAN_STRIDE;
-        const int cnt = pr[0];
-        // lane 0 owns this warp's two barriers and issues its TMA loads: box = half a row chunk (NX/4 8-byte
-        // elements), two boxes per term
+        const uint32_t bar0 = smem_u32(bars + warp * NS);
+        // this row's plan, one entry per lane: [0] = term count, [4 + t] = prefix row, [4 + MAXT + t] = weight
+        const int mine = lane < PLAN_STRIDE ? __ldg(g.plan + (size_t)y * PLAN_STRIDE + lane) : 0;
+        const int cnt = __shfl_sync(0xffffffffu, mine, 0);
+        const int c0 = sx0 / 2, c2 = img * Q + pl;
+        // two boxes per term: box = half a row chunk (NX/4 8-byte elements)
         auto issue = [&](int t) {
-            const int s = t & 1;
-            const uint32_t bar = bar0 + 8 * s;
-            const uint32_t dst = smem_u32(slot0 + s * NX);
-            const int row = pr[4 + t];
-            const int c0 = sx0 / 2, c2 = img * Q + pl;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ROW_BYTES) : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                ::"r"(dst), "l"(&tmap), "r"(c0), "r"(row), "r"(c2), "r"(bar)
-                : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                ::"r"(dst + ROW_BYTES / 2), "l"(&tmap), "r"(c0 + NX / 4), "r"(row), "r"(c2), "r"(bar)
-                : "memory");
+            const int row = __shfl_sync(0xffffffffu, mine, 4 + t);
+            const uint32_t bar = bar0 + 8 * (t % NS);
+            const uint32_t dst = smem_u32(slot0 + (t % NS) * NX);
+            if (elect_one()) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ROW_BYTES) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                    ::"r"(dst), "l"(&tmap), "r"(c0), "r"(row), "r"(c2), "r"(bar)
+                    : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                    ::"r"(dst + ROW_BYTES / 2), "l"(&tmap), "r"(c0 + NX / 4), "r"(row), "r"(c2), "r"(bar)
+                    : "memory");
+            }
         };
-        if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+        if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * k) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            issue(0);
-            if (cnt > 1) issue(1);
         }
         __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            if (k < cnt) issue(k);
         float acc[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] = 0.0f;
         for (int t = 0; t < cnt; ++t) {
-            const int s = t & 1;
-            const float wgt = __int_as_float(pr[4 + MAXT + t]);
-            mbar_wait(bar0 + 8 * s, (uint32_t)(t >> 1) & 1u);
+            const int s = t % NS;
+            const float wgt = __int_as_float(__shfl_sync(0xffffffffu, mine, 4 + MAXT + t));
+            mbar_wait(bar0 + 8 * s, (uint32_t)(t / NS) & 1u);
             const float4 *sp = reinterpret_cast<const float4 *>(slot0 + s * NX + lane * C);
             const f2 w2 = dup2(wgt);
 #pragma unroll
@@ -725,8 +745,8 @@ __global__ void __launch_bounds__(32 * pass_b_warps<SC, RB>(), SC == 1 ? 2 : 1)
                 unpack2(a01, acc[c], acc[c + 1]);
                 unpack2(a23, acc[c + 2], acc[c + 3]);
             }
-            __syncwarp();  // every lane has read the slot before lane 0 lets the next term overwrite it
-            if (lane == 0 && t + 2 < cnt) issue(t + 2);
+            __syncwarp();  // every lane has read the slot before the next term may overwrite it
+            if (t + NS < cnt) issue(t + NS);
         }
         // horizontal prefix over the strip: serial over the lane's C columns, then one warp scan of the lane totals
         float run = 0.0f;
@@ -758,85 +778,101 @@ __global__ void __launch_bounds__(32 * pass_b_warps<SC, RB>(), SC == 1 ? 2 : 1)
     if (y >= g.h) return;
 
     // the Q warps of a row share its pixels: one pixel pair per thread and step
-    const float *Prow = slots + (rr * Q * 2) * NX;  // plane k of this row: Prow + k * 2 * NX
+    const float *Prow = slots + (rr * Q * NS) * NX;  // plane k of this row: Prow + k * NS * NX
     const uint32_t *PK = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp;
     const int n_out = min(g.twe_b, g.w - sx0);
     const f2 ia2 = dup2(g.inv_area);
     const bool w_even = (g.w & 1) == 0;
-    for (int idx = 2 * (pl * 32 + lane); idx < n_out; idx += 2 * 32 * Q) {
-        const bool both = idx + 1 < n_out;
-        const int i = g.rh + idx;
-        const int x = sx0 + idx;
-        const uint2 gw = *reinterpret_cast<const uint2 *>(PK + g.rh + x);
-        const f2 i0 = b2f2(gw.x, gw.y, 0, false), i1 = b2f2(gw.x, gw.y, 1, false), i2 = b2f2(gw.x, gw.y, 2, false);
-        uint32_t res0[SC], res1[SC];
-#pragma unroll
-        for (int c = 0; c < SC; ++c) {
-            f2 m[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float *Pq = Prow + (4 * c + k) * 2 * NX;
-                m[k] = mul2(sub2(pack2(Pq[i + r], Pq[i + r + 1]), pack2(Pq[i - r - 1], Pq[i - r])), ia2);
-            }
-            f2 v = m[3];
-            v = add2(v, mul2(m[0], i0));
-            v = add2(v, mul2(m[1], i1));
-            v = add2(v, mul2(m[2], i2));
-            float v0, v1;
-            unpack2(v, v0, v1);
-            res0[c] = sat_u8(v0);
-            res1[c] = sat_u8(v1);
-        }
-        if (g.store_dst) {
-            uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + x) * SC;
-            if (SC == 1) {
-                if (both && w_even)
-                    *reinterpret_cast<uint16_t *>(o) = (uint16_t)(res0[0] | (res1[0] << 8));
-                else {
-                    o[0] = (uint8_t)res0[0];
-                    if (both) o[1] = (uint8_t)res1[0];
+    auto solve_rows = [&](auto r_odd) {
+        constexpr bool R_ODD = decltype(r_odd)::value;
+        for (int idx = 2 * (pl * 32 + lane); idx < n_out; idx += 2 * 32 * Q) {
+            const bool both = idx + 1 < n_out;
+            const int i = g.rh + idx;
+            const int x = sx0 + idx;
+            const uint2 gw = *reinterpret_cast<const uint2 *>(PK + g.rh + x);
+            const f2 i0 = b2f2(gw.x, gw.y, 0, false), i1 = b2f2(gw.x, gw.y, 1, false), i2 = b2f2(gw.x, gw.y, 2, false);
+            uint32_t res0[SC], res1[SC];
+    #pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                f2 m[4];
+    #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float *Pq = Prow + (4 * c + k) * NS * NX;
+                    // (P[i+r] - P[i-r-1], P[i+r+1] - P[i-r]); i is even, so one of the two pairs is an aligned 64-bit load
+                    f2 hi, lo;
+                    if (R_ODD) {
+                        hi = pack2(Pq[i + r], Pq[i + r + 1]);
+                        lo = *reinterpret_cast<const f2 *>(Pq + i - r - 1);
+                    } else {
+                        hi = *reinterpret_cast<const f2 *>(Pq + i + r);
+                        lo = pack2(Pq[i - r - 1], Pq[i - r]);
+                    }
+                    m[k] = mul2(sub2(hi, lo), ia2);
                 }
-            } else {
-                if (both && w_even) {
-                    uint16_t *o2 = reinterpret_cast<uint16_t *>(o);
-                    o2[0] = (uint16_t)(res0[0] | (res0[1 % SC] << 8));
-                    o2[1] = (uint16_t)(res0[2 % SC] | (res1[0] << 8));
-                    o2[2] = (uint16_t)(res1[1 % SC] | (res1[2 % SC] << 8));
+                f2 v = m[3];
+                v = add2(v, mul2(m[0], i0));
+                v = add2(v, mul2(m[1], i1));
+                v = add2(v, mul2(m[2], i2));
+                float v0, v1;
+                unpack2(v, v0, v1);
+                res0[c] = sat_u8(v0);
+                res1[c] = sat_u8(v1);
+            }
+            if (g.store_dst) {
+                uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + x) * SC;
+                if (SC == 1) {
+                    if (both && w_even)
+                        *reinterpret_cast<uint16_t *>(o) = (uint16_t)(res0[0] | (res1[0] << 8));
+                    else {
+                        o[0] = (uint8_t)res0[0];
+                        if (both) o[1] = (uint8_t)res1[0];
+                    }
                 } else {
-#pragma unroll
-                    for (int c = 0; c < SC; ++c) o[c] = (uint8_t)res0[c];
-                    if (both)
-#pragma unroll
-                        for (int c = 0; c < SC; ++c) o[SC + c] = (uint8_t)res1[c];
+                    if (both && w_even) {
+                        uint16_t *o2 = reinterpret_cast<uint16_t *>(o);
+                        o2[0] = (uint16_t)(res0[0] | (res0[1 % SC] << 8));
+                        o2[1] = (uint16_t)(res0[2 % SC] | (res1[0] << 8));
+                        o2[2] = (uint16_t)(res1[1 % SC] | (res1[2 % SC] << 8));
+                    } else {
+    #pragma unroll
+                        for (int c = 0; c < SC; ++c) o[c] = (uint8_t)res0[c];
+                        if (both)
+    #pragma unroll
+                            for (int c = 0; c < SC; ++c) o[SC + c] = (uint8_t)res1[c];
+                    }
+                }
+            }
+            if (g.store_packed) {
+                // the next iteration filters this output: put it where pack_kernel would have put it, mirrored
+                // halo columns included.  Other CTAs of this launch read only the guide bytes of these words.
+                uint32_t *row = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp + (SC == 1 ? 0 : plane);
+                const uint32_t w0 = SC == 1 ? (gw.x & 0x00FFFFFFu) | (res0[0] << 24)
+                                            : res0[0] | (res0[1 % SC] << 8) | (res0[2 % SC] << 16);
+                const uint32_t w1 = SC == 1 ? (gw.y & 0x00FFFFFFu) | (res1[0] << 24)
+                                            : res1[0] | (res1[1 % SC] << 8) | (res1[2 % SC] << 16);
+                if (both)
+                    *reinterpret_cast<uint2 *>(row + g.rh + x) = make_uint2(w0, w1);
+                else
+                    row[g.rh + x] = w0;
+                if (x < g.rh || x + 1 >= g.w - g.rh) {
+    #pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (e == 1 && !both) break;
+                        const int xe = x + e;
+                        const uint32_t wv = e == 0 ? w0 : w1;
+                        const int xl = xe < g.rh ? g.rh - 1 - xe : -1;
+                        const int xr = xe >= g.w - g.rh ? g.rh + 2 * g.w - 1 - xe : -1;
+                        if (xl >= 0) row[xl] = wv;
+                        if (xr >= 0 && xr < g.wp) row[xr] = wv;
+                    }
                 }
             }
         }
-        if (g.store_packed) {
-            // the next iteration filters this output: put it where pack_kernel would have put it, mirrored
-            // halo columns included.  Other CTAs of this launch read only the guide bytes of these words.
-            uint32_t *row = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp + (SC == 1 ? 0 : plane);
-            const uint32_t w0 = SC == 1 ? (gw.x & 0x00FFFFFFu) | (res0[0] << 24)
-                                        : res0[0] | (res0[1 % SC] << 8) | (res0[2 % SC] << 16);
-            const uint32_t w1 = SC == 1 ? (gw.y & 0x00FFFFFFu) | (res1[0] << 24)
-                                        : res1[0] | (res1[1 % SC] << 8) | (res1[2 % SC] << 16);
-            if (both)
-                *reinterpret_cast<uint2 *>(row + g.rh + x) = make_uint2(w0, w1);
-            else
-                row[g.rh + x] = w0;
-            if (x < g.rh || x + 1 >= g.w - g.rh) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    if (e == 1 && !both) break;
-                    const int xe = x + e;
-                    const uint32_t wv = e == 0 ? w0 : w1;
-                    const int xl = xe < g.rh ? g.rh - 1 - xe : -1;
-                    const int xr = xe >= g.w - g.rh ? g.rh + 2 * g.w - 1 - xe : -1;
-                    if (xl >= 0) row[xl] = wv;
-                    if (xr >= 0 && xr < g.wp) row[xr] = wv;
-                }
-            }
-        }
-    }
+    };
+    if (r & 1)
+        solve_rows(std::true_type{});
+    else
+        solve_rows(std::false_type{});
 }
 
 // ---- host -------------------------------------------------------------------------------------------
@@ -955,18 +991,18 @@ struct DeviceOnce {
     bool done[64] = {};
 };
 
-template <int SC, int CB>
+template <int SC, int CB, int RB, int NS>
 static int launch_b(const Args &a, const Plan &p, cudaStream_t st)
 {
-    constexpr int RB = SC == 1 ? 4 : 1, NW = pass_b_warps<SC, RB>(), NX = 32 * CB;
-    constexpr size_t smem = (size_t)NW * 2 * NX * sizeof(float) + (size_t)NW * 2 * sizeof(uint64_t);
+    constexpr int NW = pass_b_warps<SC, RB>(), NX = 32 * CB;
+    constexpr size_t smem = (size_t)NW * NS * NX * sizeof(float) + (size_t)NW * NS * sizeof(uint64_t);
     static DeviceOnce once;
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
     {
         std::lock_guard<std::mutex> lock(once.mu);
         if (!once.done[dev & 63]) {
-            RF_CUDA_TRY(cudaFuncSetAttribute(pass_b_kernel<SC, CB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RF_CUDA_TRY(cudaFuncSetAttribute(pass_b_kernel<SC, CB, RB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             once.done[dev & 63] = true;
         }
     }
@@ -974,7 +1010,7 @@ static int launch_b(const Args &a, const Plan &p, cudaStream_t st)
     const int rc = make_tensor_map(&tm, a.ab, a.wp, a.h, (size_t)a.n * 4 * SC, NX);
     if (rc != RF_OK) return rc;
     const dim3 grid((a.h + RB - 1) / RB, p.strips_b, a.n);
-    pass_b_kernel<SC, CB, RB><<<grid, 32 * NW, smem, st>>>(tm, a);
+    pass_b_kernel<SC, CB, RB, NS><<<grid, 32 * NW, smem, st>>>(tm, a);
     RF_LAUNCH_CHECK("gf2::pass_b_kernel");
     return RF_OK;
 }
@@ -1036,7 +1072,14 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
         RF_LAUNCH_CHECK("gf2::pass_a_kernel");
         a.store_dst = last ? 1 : 0;
         a.store_packed = last ? 0 : 1;
-        const int rc = p.CB == 12 ? launch_b<SC, 12>(a, p, st) : launch_b<SC, 20>(a, p, st);
+        static const int ns_env = env_int("RF_GF2_NS");
+        int rc;
+        if (SC == 1 && ns_env == 3)
+            rc = p.CB == 12 ? launch_b<SC, 12, 1, 3>(a, p, st) : launch_b<SC, 20, 1, 3>(a, p, st);
+        else if (SC == 1 && ns_env == 4)
+            rc = p.CB == 12 ? launch_b<SC, 12, 1, 4>(a, p, st) : launch_b<SC, 20, 1, 4>(a, p, st);
+        else
+            rc = p.CB == 12 ? launch_b<SC, 12, 1, 2>(a, p, st) : launch_b<SC, 20, 1, 2>(a, p, st);
         if (rc != RF_OK) return rc;
     }
     return RF_OK;
