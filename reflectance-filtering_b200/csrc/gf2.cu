@@ -233,35 +233,6 @@ struct RowRaw {
     uint32_t w1[SC == 1 ? 1 : C];
 };
 
-template <int SC, int C>
-__device__ __forceinline__ RowRaw<SC, C> prefetch_row(const uint32_t *plane0, size_t plane_stride, int wp, int yy, int xp0)
-{
-    RowRaw<SC, C> r;
-    const uint4 *p = reinterpret_cast<const uint4 *>(plane0 + (size_t)yy * wp + xp0);
-#pragma unroll
-    for (int c = 0; c < C; c += 4) {
-        const uint4 t = __ldg(p + c / 4);
-        r.w0[c] = t.x;
-        r.w0[c + 1] = t.y;
-        r.w0[c + 2] = t.z;
-        r.w0[c + 3] = t.w;
-    }
-    if (SC == 3) {
-        const uint4 *q = reinterpret_cast<const uint4 *>(plane0 + plane_stride + (size_t)yy * wp + xp0);
-#pragma unroll
-        for (int c = 0; c < (SC == 1 ? 0 : C); c += 4) {
-            const uint4 t = __ldg(q + c / 4);
-            r.w1[c] = t.x;
-            r.w1[c + 1] = t.y;
-            r.w1[c + 2] = t.z;
-            r.w1[c + 3] = t.w;
-        }
-    } else {
-        r.w1[0] = 0u;
-    }
-    return r;
-}
-
 // (byte of pixel c, byte of pixel c+1) -> packed float pair, optionally negated: PRMT builds 2^23 + b in each half,
 // one packed add (or fused negate-add) removes the bias for both
 __device__ __forceinline__ unsigned long long b2f2(uint32_t w0, uint32_t w1, int byte, bool negate)
@@ -328,16 +299,10 @@ __device__ __forceinline__ void scan_store(const float (&V)[NQG][C], uint32_t *P
         uint32_t pre[C];
         uint32_t run = 0;
 #pragma unroll
-        for (int c = 0; c < C; c += 2) {
-            // integer value + 0x4B000000 per element; the float add on two columns at once
-            unsigned long long b2;
-            asm("add.rn.f32x2 %0, %1, %2;" : "=l"(b2) : "l"(pack2(V[q][c], V[q][c + 1])), "l"(pack2(8388608.0f, 8388608.0f)));
-            float b0, b1;
-            unpack2(b2, b0, b1);
-            run += __float_as_uint(b0);
+        for (int c = 0; c < C; ++c) {
+            // V = 2^23 + (window sum): its bit pattern is 0x4B000000 + the integer, no conversion needed
+            run += __float_as_uint(V[q][c]);
             pre[c] = run;
-            run += __float_as_uint(b1);
-            pre[c + 1] = run;
         }
         uint32_t incl = run;
 #pragma unroll
@@ -402,9 +367,19 @@ enum Mode { FULL = 0, FULL_STORE = 1, SRC_ONLY = 2 };
 // window sums of the pixel pair (i, i+1) -> box means.  Sums of single channels stay below 2^23: exact
 // integer->float on the FMA pipe.  (Four 32-bit loads: which of the two index pairs is 8-byte aligned depends on
 // the parity of the radius.)
+template <bool R_ODD>
 __device__ __forceinline__ f2 box_mean2(const uint32_t *Pq, int i, int r, uint32_t bias, bool linear, f2 inv_area2)
 {
-    const uint32_t d0 = Pq[i + r] - Pq[i - r - 1] - bias, d1 = Pq[i + r + 1] - Pq[i - r] - bias;
+    // i is even: P[i-r-1], P[i-r] (odd radius) or P[i+r], P[i+r+1] (even radius) is one aligned 64-bit load
+    uint32_t h0, h1, l0, l1;
+    if (R_ODD) {
+        const uint2 lo = *reinterpret_cast<const uint2 *>(Pq + i - r - 1);
+        l0 = lo.x, l1 = lo.y, h0 = Pq[i + r], h1 = Pq[i + r + 1];
+    } else {
+        const uint2 hi = *reinterpret_cast<const uint2 *>(Pq + i + r);
+        h0 = hi.x, h1 = hi.y, l0 = Pq[i - r - 1], l1 = Pq[i - r];
+    }
+    const uint32_t d0 = h0 - l0 - bias, d1 = h1 - l1 - bias;
     f2 sf;
     if (linear)
         sf = add2(pack2(__uint_as_float(d0 | 0x4B000000u), __uint_as_float(d1 | 0x4B000000u)), dup2(-8388608.0f));
@@ -487,37 +462,125 @@ __device__ __forceinline__ void st_pair(float *p, f2 v, bool both)
     }
 }
 
+// ---- mbarrier / TMA helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+}
+
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
 // ---- pass A ---------------------------------------------------------------------------------------
 // MODE FULL: all 9 + 4*SC quantities.  FULL_STORE: the same, and the guide statistics go to g.gstat.
 // SRC_ONLY: only the 4*SC source quantities; mean(I) and the inverse covariance come from g.gstat.
+//
+// The packed rows arrive through TMA: an elected lane of warp 0 requests, RING-1 steps ahead, the row that enters
+// the vertical window and (once rows are emitted) the row that leaves it, as one box of NX pixels per plane
+// (3-D map of the packed planes; columns beyond the padded row are zero-filled and only feed prefixes right of
+// every window).  Every warp reads its lanes' chunks from the ring with conflict-free 128-bit loads and releases
+// the slot through an mbarrier, so DRAM latency is hidden by the ring, not by resident warps, and no row lives
+// in registers across steps.
+constexpr int RING = 4;
+
+template <int SC, int C>
+__device__ __forceinline__ RowRaw<SC, C> read_row(const uint32_t *slot, int lane)
+{
+    constexpr int NX = 32 * C;
+    RowRaw<SC, C> r;
+    const uint4 *p = reinterpret_cast<const uint4 *>(slot + lane * C);
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+        const uint4 t = p[c / 4];
+        r.w0[c] = t.x, r.w0[c + 1] = t.y, r.w0[c + 2] = t.z, r.w0[c + 3] = t.w;
+    }
+    if (SC == 3) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(slot + NX + lane * C);
+#pragma unroll
+        for (int c = 0; c < (SC == 1 ? 0 : C); c += 4) {
+            const uint4 t = q[c / 4];
+            r.w1[c] = t.x, r.w1[c + 1] = t.y, r.w1[c + 2] = t.z, r.w1[c + 3] = t.w;
+        }
+    } else {
+        r.w1[0] = 0u;
+    }
+    return r;
+}
+
+template <int SC, int C>
+__host__ __device__ constexpr size_t pass_a_smem(int q)
+{
+    // prefix rows [2][q][NX], ring [RING][2][NP][NX], 2 * RING mbarriers
+    return ((size_t)2 * q * 32 * C + (size_t)RING * 2 * (SC == 1 ? 1 : 2) * 32 * C) * 4 + 2 * RING * 8;
+}
+
 template <int SC, int C, int MODE>
-__global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1) pass_a_kernel(const Args g)
+__global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
+    pass_a_kernel(const __grid_constant__ CUtensorMap tmap, const Args g)
 {
     constexpr int QB = MODE == SRC_ONLY ? 9 : 0;  // first quantity this kernel accumulates
-    constexpr int Q = 9 + 4 * SC - QB, NX = 32 * C, NT = 32 * n_groups<SC>(), NP = SC == 1 ? 1 : 2;
-    extern __shared__ __align__(16) uint32_t pbuf[];  // [2][Q][NX]
-    const int tid = threadIdx.x, lane = tid & 31, group = tid >> 5;
+    constexpr int Q = 9 + 4 * SC - QB, NX = 32 * C, NP = SC == 1 ? 1 : 2, NG = n_groups<SC>();
+    constexpr uint32_t ROW_BYTES = NP * NX * 4;
+    extern __shared__ __align__(128) uint32_t pbuf[];  // [2][Q][NX] | ring [RING][2][NP][NX] | full[RING], empty[RING]
+    uint32_t *ring = pbuf + 2 * Q * NX;
+    const uint32_t bars = smem_u32(ring + RING * 2 * NP * NX);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int group = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int img = blockIdx.z;
-    const int sx0 = blockIdx.x * g.twe;  // first output column of the strip (image coordinates)
+    const int sx0 = blockIdx.x * g.twe;  // first output column of the strip (image coordinates) = padded
+                                         // coordinate of the strip's first column (origin sx0 - rh, + rh padding)
     const int y0 = blockIdx.y * g.seg_rows;
     const int y1 = min(g.h, y0 + g.seg_rows);
     const size_t plane = (size_t)g.h * g.wp;
-    const uint32_t *PK = g.packed + (size_t)img * NP * plane;
     const int r = g.r;
     const int n_out = min(g.twe, g.w - sx0);  // <= 2 * NT: every thread solves at most one pixel pair per row
     const uint32_t bias = (uint32_t)(2 * r + 1) * 0x4B000000u;  // what the biased elements add to a window
-    // padded coordinate of this lane's first column is sx0 + lane*C (strip origin sx0 - rh, plus the rh
-    // offset of the padding).  Lanes whose chunk would start beyond the padded row re-read the last
-    // chunk: their prefixes lie right of every window of this strip and are never used.
-    const int xp0c = min(sx0 + lane * C, g.wp - C);
     float *GS = MODE == FULL ? nullptr : g.gstat + (size_t)img * 9 * plane;
     const f2 ia2 = dup2(g.inv_area);
 
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < RING; ++k) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8 * k) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * (RING + k)), "r"(NG) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // vertical window sums, carried as 2^23 + sum (exact integers below 2^24): the scan reads their bit patterns
     float V[NQG][C];
 #pragma unroll
     for (int q = 0; q < NQG; ++q)
 #pragma unroll
-        for (int c = 0; c < C; ++c) V[q][c] = 0.0f;
+        for (int c = 0; c < C; ++c) V[q][c] = 8388608.0f;
 
     // this thread's pixel pair: output columns sx0 + idx, sx0 + idx + 1 of every row of the segment
     const int idx = 2 * tid;
@@ -525,6 +588,7 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1) pass_a_k
     const bool both = idx + 1 < n_out;  // false: the image ends between the two (odd width)
     const int x = sx0 + idx;
     const bool edge = x < g.rh || x + 1 >= g.w - g.rh;  // has mirrored copies in the halo columns
+    float *const ab0 = g.ab + (size_t)img * SC * 4 * plane;
     // vertical prefix sums of the coefficients down the rows of this segment (what pass B consumes)
     f2 pv[SC][4];
 #pragma unroll
@@ -533,7 +597,8 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1) pass_a_k
         for (int k = 0; k < 4; ++k) pv[c][k] = 0ull;
 
     // the per-pixel solve of one output row from its prefixes P (and, in SRC_ONLY mode, the statistics gs)
-    auto math_row = [&](const int y, const uint32_t *P, const f2 *gs) {
+    auto math_row = [&](auto r_odd, const int y, const uint32_t *P, const f2 *gs) {
+        constexpr bool R_ODD = decltype(r_odd)::value;
         if (!active) return;
         const int i = g.rh + idx;
         const size_t row_off = (size_t)y * g.wp;
@@ -546,7 +611,7 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1) pass_a_k
         } else {
             f2 m[9];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) m[q] = box_mean2(P + q * NX, i, r, bias, q_is_linear(q), ia2);
+            for (int q = 0; q < 9; ++q) m[q] = box_mean2<R_ODD>(P + q * NX, i, r, bias, q_is_linear(q), ia2);
             guide_inverse2(m, g.eps, inv);
             mi[0] = m[0];
             mi[1] = m[1];
@@ -564,10 +629,10 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1) pass_a_k
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int q = 9 + 4 * c + k;
-                ms[k] = box_mean2(P + (q - QB) * NX, i, r, bias, k == 0, ia2);
+                ms[k] = box_mean2<R_ODD>(P + (q - QB) * NX, i, r, bias, k == 0, ia2);
             }
             solve_source2(ms, mi, inv, v);
-            float *o = g.ab + ((size_t)(img * SC + c) * 4) * plane + row_off;
+            float *o = ab0 + (size_t)c * 4 * plane + row_off;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 pv[c][k] = add2(pv[c][k], v[k]);
@@ -600,77 +665,96 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1) pass_a_k
         for (int j = 0; j < 9; ++j) gs[j] = __ldg(reinterpret_cast<const f2 *>(p + j * plane));
     };
 
-    // One loop over the rows entering the window: steps 0..2r-1 only warm the vertical sums up, every later
-    // step also emits a row.  Software-pipelined by one row: between two barriers a warp scans row y AND
-    // solves row y-1 (whose prefixes all warps stored before the previous barrier), so the shuffle-latency-
-    // bound scan overlaps the arithmetic of the solve.  Rows are requested one step ahead of their use.
-    RowRaw<SC, C> cur_in = prefetch_row<SC, C>(PK, plane, g.wp, reflect(y0 - r, g.h), xp0c);
-    RowRaw<SC, C> cur_out = cur_in;
+    // Step t: the row y0 - r + t enters the window; from t = 2r on, output row y = y0 + t - 2r is emitted and the
+    // row y - r leaves afterwards.  Warp 0 requests the rows of step t (warp-uniform code, elected lane).
     const int n_steps = 2 * r + (y1 - y0);
+    auto request = [&](const int t) {
+        const int s = t % RING;
+        if (t >= RING) mbar_wait(bars + 8 * (RING + s), (uint32_t)(t / RING - 1) & 1u);  // every warp released use t - RING
+        const bool has_out = t >= 2 * r;
+        const int yin = reflect(y0 - r + t, g.h);
+        const int yout = has_out ? reflect(y0 + t - 3 * r, g.h) : 0;
+        if (elect_one()) {
+            const uint32_t full = bars + 8 * s;
+            const uint32_t dst = smem_u32(ring + (s * 2) * NP * NX);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full),
+                         "r"(has_out ? 2 * ROW_BYTES : ROW_BYTES)
+                         : "memory");
+            tma_load_3d(dst, &tmap, sx0 / 2, yin, img * NP, full);
+            if (has_out) tma_load_3d(dst + ROW_BYTES, &tmap, sx0 / 2, yout, img * NP, full);
+        }
+    };
+    auto release = [&](const int t) {
+        __syncwarp();
+        if (elect_one())
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (RING + t % RING)) : "memory");
+    };
+    if (group == 0)
+        for (int t = 0; t < RING - 1 && t < n_steps; ++t) request(t);
+
+    // Software-pipelined by one row: between two barriers a warp scans row y AND solves row y-1 (whose prefixes
+    // all warps stored before the previous barrier), so the shuffle-latency-bound scan overlaps the arithmetic
+    // of the solve.
+    const bool r_is_odd = (r & 1) != 0;
     f2 gs[MODE == SRC_ONLY ? 9 : 1];
     for (int t = 0; t < n_steps; ++t) {
-        const RowRaw<SC, C> nxt_in = prefetch_row<SC, C>(PK, plane, g.wp, reflect(y0 - r + t + 1, g.h), xp0c);
+        if (group == 0 && t + RING - 1 < n_steps) request(t + RING - 1);
         // cached guide statistics of the pixels this thread solves in this step (row y-1): requested before
         // the accumulate / scan work so that their DRAM latency is hidden
         if (MODE == SRC_ONLY && t > 2 * r) load_stats(y0 + t - 2 * r - 1, gs);
-        if (MODE == SRC_ONLY) {
-            RF_GF2_DISPATCH_SRC(accumulate, V, cur_in, 1.0f)
-        } else {
-            RF_GF2_DISPATCH(accumulate, V, cur_in, 1.0f)
+        const uint32_t *slot = ring + ((t % RING) * 2) * NP * NX;
+        mbar_wait(bars + 8 * (t % RING), (uint32_t)(t / RING) & 1u);
+        {
+            const RowRaw<SC, C> row_in = read_row<SC, C>(slot, lane);
+            if (t < 2 * r) release(t);
+            if (MODE == SRC_ONLY) {
+                RF_GF2_DISPATCH_SRC(accumulate, V, row_in, 1.0f)
+            } else {
+                RF_GF2_DISPATCH(accumulate, V, row_in, 1.0f)
+            }
         }
-        cur_in = nxt_in;
         if (t < 2 * r) continue;
         const int y = y0 + t - 2 * r;
-        const RowRaw<SC, C> nxt_out = prefetch_row<SC, C>(PK, plane, g.wp, reflect(y + 1 - r, g.h), xp0c);
         uint32_t *P = pbuf + ((y - y0) & 1) * (Q * NX);
         if (MODE == SRC_ONLY) {
             RF_GF2_DISPATCH_SRC(scan_store, V, P, NX, lane)
-            RF_GF2_DISPATCH_SRC(accumulate, V, cur_out, -1.0f)
         } else {
             RF_GF2_DISPATCH(scan_store, V, P, NX, lane)
-            RF_GF2_DISPATCH(accumulate, V, cur_out, -1.0f)
         }
-        cur_out = nxt_out;
-        if (y > y0) math_row(y - 1, pbuf + ((y - 1 - y0) & 1) * (Q * NX), gs);
+        {
+            const RowRaw<SC, C> row_out = read_row<SC, C>(slot + NP * NX, lane);
+            release(t);
+            if (MODE == SRC_ONLY) {
+                RF_GF2_DISPATCH_SRC(accumulate, V, row_out, -1.0f)
+            } else {
+                RF_GF2_DISPATCH(accumulate, V, row_out, -1.0f)
+            }
+        }
+        if (y > y0) {
+            const uint32_t *Pm = pbuf + ((y - 1 - y0) & 1) * (Q * NX);
+            if (r_is_odd)
+                math_row(std::true_type{}, y - 1, Pm, gs);
+            else
+                math_row(std::false_type{}, y - 1, Pm, gs);
+        }
         // One barrier per row: the prefixes of row y are visible to everyone after it, and everyone has
         // finished reading the other buffer (row y-1), which the next step overwrites.
         __syncthreads();
     }
     if (MODE == SRC_ONLY) load_stats(y1 - 1, gs);
-    math_row(y1 - 1, pbuf + ((y1 - 1 - y0) & 1) * (Q * NX), gs);
+    {
+        const uint32_t *Pm = pbuf + ((y1 - 1 - y0) & 1) * (Q * NX);
+        if (r_is_odd)
+            math_row(std::true_type{}, y1 - 1, Pm, gs);
+        else
+            math_row(std::false_type{}, y1 - 1, Pm, gs);
+    }
 }
 
 // ---- pass B ---------------------------------------------------------------------------------------
 // One warp per (output row, coefficient plane), RB rows per CTA.  No state is carried from row to row.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    while (!done)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-}
-
 template <int SC, int RB>
 __host__ __device__ constexpr int pass_b_warps() { return 4 * SC * RB; }
-
-// one lane of a converged warp
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
 
 // The whole issue path of pass B is warp-uniform: the warp index, the output row and the row plan are broadcast
 // values, and the loads are issued by an elected lane.  (Issued from `if (lane == 0)` the compiler wrapped every
@@ -969,14 +1053,14 @@ static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
     return fn;
 }
 
-// 3-D map of the prefix planes as 8-byte elements: (wp / 2, h, planes); box = half a lane-chunk row (nx / 4 elements)
-static int make_tensor_map(CUtensorMap *tm, float *base, int wp, int h, size_t planes, int nx)
+// 3-D map of 32-bit planes [planes][h][wp] as 8-byte elements: (wp / 2, h, planes); box = (box_x, 1, box_planes)
+static int make_tensor_map(CUtensorMap *tm, void *base, int wp, int h, size_t planes, int box_x, int box_planes)
 {
     PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
     if (!enc) return fail(RF_ECUDA, "gf2: cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[3] = {(cuuint64_t)wp / 2, (cuuint64_t)h, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)wp * 4, (cuuint64_t)h * wp * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)nx / 4, 1, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_x, 1, (cuuint32_t)box_planes};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, base, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1007,7 +1091,7 @@ static int launch_b(const Args &a, const Plan &p, cudaStream_t st)
         }
     }
     CUtensorMap tm;
-    const int rc = make_tensor_map(&tm, a.ab, a.wp, a.h, (size_t)a.n * 4 * SC, NX);
+    const int rc = make_tensor_map(&tm, a.ab, a.wp, a.h, (size_t)a.n * 4 * SC, NX / 4, 1);
     if (rc != RF_OK) return rc;
     const dim3 grid((a.h + RB - 1) / RB, p.strips_b, a.n);
     pass_b_kernel<SC, CB, RB, NS><<<grid, 32 * NW, smem, st>>>(tm, a);
@@ -1019,8 +1103,9 @@ template <int SC, int C>
 static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
 {
     constexpr int QA_ = 9 + 4 * SC, QS_ = 4 * SC, NX = 32 * C, NTA = 32 * n_groups<SC>();
-    const size_t smem_a = (size_t)2 * QA_ * NX * sizeof(uint32_t);
-    const size_t smem_s = (size_t)2 * QS_ * NX * sizeof(uint32_t);
+    constexpr int NP = SC == 1 ? 1 : 2;
+    const size_t smem_a = pass_a_smem<SC, C>(QA_);
+    const size_t smem_s = pass_a_smem<SC, C>(QS_);
     static DeviceOnce once;
     static int occ_a = 1;
     int dev = 0;
@@ -1035,6 +1120,12 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
             if (occ_a < 1) occ_a = 1;
             once.done[dev & 63] = true;
         }
+    }
+    // packed rows as TMA boxes: one strip chunk (NX pixels) of every plane of an image
+    CUtensorMap tm_pk;
+    {
+        const int rc = make_tensor_map(&tm_pk, a.packed, a.wp, a.h, (size_t)a.n * NP, NX / 2, NP);
+        if (rc != RF_OK) return rc;
     }
     dim3 pgrid((a.wp + 255) / 256, (a.h + PACK_ROWS - 1) / PACK_ROWS, a.n);
     pack_kernel<SC><<<pgrid, 256, 0, st>>>(a);
@@ -1063,11 +1154,11 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
         const bool last = it == iterations - 1;
         if (it == 0) {
             if (iterations > 1)
-                pass_a_kernel<SC, C, FULL_STORE><<<grid_a, NTA, smem_a, st>>>(a);
+                pass_a_kernel<SC, C, FULL_STORE><<<grid_a, NTA, smem_a, st>>>(tm_pk, a);
             else
-                pass_a_kernel<SC, C, FULL><<<grid_a, NTA, smem_a, st>>>(a);
+                pass_a_kernel<SC, C, FULL><<<grid_a, NTA, smem_a, st>>>(tm_pk, a);
         } else {
-            pass_a_kernel<SC, C, SRC_ONLY><<<grid_a, NTA, smem_s, st>>>(a);
+            pass_a_kernel<SC, C, SRC_ONLY><<<grid_a, NTA, smem_s, st>>>(tm_pk, a);
         }
         RF_LAUNCH_CHECK("gf2::pass_a_kernel");
         a.store_dst = last ? 1 : 0;
