@@ -508,7 +508,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
 // every window).  Every warp reads its lanes' chunks from the ring with conflict-free 128-bit loads and releases
 // the slot through an mbarrier, so DRAM latency is hidden by the ring, not by resident warps, and no row lives
 // in registers across steps.
-constexpr int RING = 4;
+// ring depth in steps: the statistics of SRC_ONLY make its slots four times larger, three of them keep four CTAs per SM
+template <int MODE>
+__host__ __device__ constexpr int ring_depth() { return MODE == 2 ? 3 : 4; }
 
 template <int SC, int C>
 __device__ __forceinline__ RowRaw<SC, C> read_row(const uint32_t *slot, int lane)
@@ -534,23 +536,34 @@ __device__ __forceinline__ RowRaw<SC, C> read_row(const uint32_t *slot, int lane
     return r;
 }
 
-template <int SC, int C>
-__host__ __device__ constexpr size_t pass_a_smem(int q)
+// bytes of one ring slot: entering row + leaving row (NP planes of NX pixels each), and in SRC_ONLY mode the nine
+// cached statistics planes of the 2 * threads pixels the CTA solves per row
+template <int SC, int C, int MODE>
+__host__ __device__ constexpr size_t pass_a_slot_bytes()
 {
-    // prefix rows [2][q][NX], ring [RING][2][NP][NX], 2 * RING mbarriers
-    return ((size_t)2 * q * 32 * C + (size_t)RING * 2 * (SC == 1 ? 1 : 2) * 32 * C) * 4 + 2 * RING * 8;
+    return (size_t)2 * (SC == 1 ? 1 : 2) * 32 * C * 4 + (MODE == 2 ? (size_t)9 * 2 * 32 * (SC == 1 ? 4 : 6) * 4 : 0);
+}
+template <int SC, int C, int MODE>
+__host__ __device__ constexpr size_t pass_a_smem()
+{
+    // prefix rows [2][q][NX], ring of RING slots, 2 * RING mbarriers
+    return (size_t)2 * (MODE == 2 ? 4 * SC : 9 + 4 * SC) * 32 * C * 4 + ring_depth<MODE>() * pass_a_slot_bytes<SC, C, MODE>() +
+           2 * ring_depth<MODE>() * 8;
 }
 
 template <int SC, int C, int MODE>
 __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
-    pass_a_kernel(const __grid_constant__ CUtensorMap tmap, const Args g)
+    pass_a_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_gs, const Args g)
 {
     constexpr int QB = MODE == SRC_ONLY ? 9 : 0;  // first quantity this kernel accumulates
-    constexpr int Q = 9 + 4 * SC - QB, NX = 32 * C, NP = SC == 1 ? 1 : 2, NG = n_groups<SC>();
-    constexpr uint32_t ROW_BYTES = NP * NX * 4;
-    extern __shared__ __align__(128) uint32_t pbuf[];  // [2][Q][NX] | ring [RING][2][NP][NX] | full[RING], empty[RING]
+    constexpr int Q = 9 + 4 * SC - QB, NX = 32 * C, NP = SC == 1 ? 1 : 2, NG = n_groups<SC>(), NT = 32 * NG;
+    constexpr int RING = ring_depth<MODE>();
+    constexpr uint32_t ROW_BYTES = NP * NX * 4, GS_BYTES = 9 * 2 * NT * 4;
+    constexpr uint32_t SLOT_WORDS = (uint32_t)(pass_a_slot_bytes<SC, C, MODE>() / 4);
+    // [2][Q][NX] prefixes | ring [RING] x { in [NP][NX], out [NP][NX], (SRC_ONLY) stats [9][2 * NT] } | full[RING], empty[RING]
+    extern __shared__ __align__(128) uint32_t pbuf[];
     uint32_t *ring = pbuf + 2 * Q * NX;
-    const uint32_t bars = smem_u32(ring + RING * 2 * NP * NX);
+    const uint32_t bars = smem_u32(ring + RING * SLOT_WORDS);
     const int tid = threadIdx.x, lane = tid & 31;
     const int group = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int img = blockIdx.z;
@@ -658,30 +671,36 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
             }
         }
     };
-    auto load_stats = [&](const int y, f2 *gs) {
-        if (!active) return;
-        const float *p = GS + (size_t)y * g.wp + g.rh + x;
+    // SRC_ONLY: the statistics of this thread's pixel pair, from the slot of step t
+    auto load_stats = [&](const int t, f2 *gs) {
+        const f2 *p = reinterpret_cast<const f2 *>(ring + (t % RING) * SLOT_WORDS + 2 * NP * NX) + tid;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) gs[j] = __ldg(reinterpret_cast<const f2 *>(p + j * plane));
+        for (int j = 0; j < 9; ++j) gs[j] = p[j * NT];
     };
 
     // Step t: the row y0 - r + t enters the window; from t = 2r on, output row y = y0 + t - 2r is emitted and the
-    // row y - r leaves afterwards.  Warp 0 requests the rows of step t (warp-uniform code, elected lane).
+    // row y - r leaves afterwards; from t = 2r + 1 on, row y - 1 is solved (SRC_ONLY: with its cached statistics,
+    // which travel in the same slot; the last row is solved in a step of its own, t = n_steps).  Warp 0 requests
+    // the data of step t (warp-uniform code, elected lane).
     const int n_steps = 2 * r + (y1 - y0);
+    const int n_req = MODE == SRC_ONLY ? n_steps + 1 : n_steps;
     auto request = [&](const int t) {
         const int s = t % RING;
         if (t >= RING) mbar_wait(bars + 8 * (RING + s), (uint32_t)(t / RING - 1) & 1u);  // every warp released use t - RING
-        const bool has_out = t >= 2 * r;
+        const bool has_in = t < n_steps;
+        const bool has_out = t >= 2 * r && has_in;
+        const bool has_gs = MODE == SRC_ONLY && t > 2 * r;
         const int yin = reflect(y0 - r + t, g.h);
         const int yout = has_out ? reflect(y0 + t - 3 * r, g.h) : 0;
         if (elect_one()) {
             const uint32_t full = bars + 8 * s;
-            const uint32_t dst = smem_u32(ring + (s * 2) * NP * NX);
+            const uint32_t dst = smem_u32(ring + s * SLOT_WORDS);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full),
-                         "r"(has_out ? 2 * ROW_BYTES : ROW_BYTES)
+                         "r"((has_in ? ROW_BYTES : 0u) + (has_out ? ROW_BYTES : 0u) + (has_gs ? GS_BYTES : 0u))
                          : "memory");
-            tma_load_3d(dst, &tmap, sx0 / 2, yin, img * NP, full);
+            if (has_in) tma_load_3d(dst, &tmap, sx0 / 2, yin, img * NP, full);
             if (has_out) tma_load_3d(dst + ROW_BYTES, &tmap, sx0 / 2, yout, img * NP, full);
+            if (has_gs) tma_load_3d(dst + 2 * ROW_BYTES, &tmap_gs, (g.rh + sx0) / 2, y0 + t - 2 * r - 1, img * 9, full);
         }
     };
     auto release = [&](const int t) {
@@ -690,7 +709,7 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (RING + t % RING)) : "memory");
     };
     if (group == 0)
-        for (int t = 0; t < RING - 1 && t < n_steps; ++t) request(t);
+        for (int t = 0; t < RING - 1 && t < n_req; ++t) request(t);
 
     // Software-pipelined by one row: between two barriers a warp scans row y AND solves row y-1 (whose prefixes
     // all warps stored before the previous barrier), so the shuffle-latency-bound scan overlaps the arithmetic
@@ -698,11 +717,8 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
     const bool r_is_odd = (r & 1) != 0;
     f2 gs[MODE == SRC_ONLY ? 9 : 1];
     for (int t = 0; t < n_steps; ++t) {
-        if (group == 0 && t + RING - 1 < n_steps) request(t + RING - 1);
-        // cached guide statistics of the pixels this thread solves in this step (row y-1): requested before
-        // the accumulate / scan work so that their DRAM latency is hidden
-        if (MODE == SRC_ONLY && t > 2 * r) load_stats(y0 + t - 2 * r - 1, gs);
-        const uint32_t *slot = ring + ((t % RING) * 2) * NP * NX;
+        if (group == 0 && t + RING - 1 < n_req) request(t + RING - 1);
+        const uint32_t *slot = ring + (t % RING) * SLOT_WORDS;
         mbar_wait(bars + 8 * (t % RING), (uint32_t)(t / RING) & 1u);
         {
             const RowRaw<SC, C> row_in = read_row<SC, C>(slot, lane);
@@ -723,7 +739,7 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
         }
         {
             const RowRaw<SC, C> row_out = read_row<SC, C>(slot + NP * NX, lane);
-            release(t);
+            if (MODE != SRC_ONLY) release(t);
             if (MODE == SRC_ONLY) {
                 RF_GF2_DISPATCH_SRC(accumulate, V, row_out, -1.0f)
             } else {
@@ -732,16 +748,21 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
         }
         if (y > y0) {
             const uint32_t *Pm = pbuf + ((y - 1 - y0) & 1) * (Q * NX);
+            if (MODE == SRC_ONLY) load_stats(t, gs);
             if (r_is_odd)
                 math_row(std::true_type{}, y - 1, Pm, gs);
             else
                 math_row(std::false_type{}, y - 1, Pm, gs);
         }
+        if (MODE == SRC_ONLY) release(t);
         // One barrier per row: the prefixes of row y are visible to everyone after it, and everyone has
         // finished reading the other buffer (row y-1), which the next step overwrites.
         __syncthreads();
     }
-    if (MODE == SRC_ONLY) load_stats(y1 - 1, gs);
+    if (MODE == SRC_ONLY) {
+        mbar_wait(bars + 8 * (n_steps % RING), (uint32_t)(n_steps / RING) & 1u);
+        load_stats(n_steps, gs);
+    }
     {
         const uint32_t *Pm = pbuf + ((y1 - 1 - y0) & 1) * (Q * NX);
         if (r_is_odd)
@@ -1102,10 +1123,10 @@ static int launch_b(const Args &a, const Plan &p, cudaStream_t st)
 template <int SC, int C>
 static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
 {
-    constexpr int QA_ = 9 + 4 * SC, QS_ = 4 * SC, NX = 32 * C, NTA = 32 * n_groups<SC>();
+    constexpr int NX = 32 * C, NTA = 32 * n_groups<SC>();
     constexpr int NP = SC == 1 ? 1 : 2;
-    const size_t smem_a = pass_a_smem<SC, C>(QA_);
-    const size_t smem_s = pass_a_smem<SC, C>(QS_);
+    const size_t smem_a = pass_a_smem<SC, C, FULL>();
+    const size_t smem_s = pass_a_smem<SC, C, SRC_ONLY>();
     static DeviceOnce once;
     static int occ_a = 1;
     int dev = 0;
@@ -1125,6 +1146,12 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
     CUtensorMap tm_pk;
     {
         const int rc = make_tensor_map(&tm_pk, a.packed, a.wp, a.h, (size_t)a.n * NP, NX / 2, NP);
+        if (rc != RF_OK) return rc;
+    }
+    // cached statistics of the pixel pairs a CTA solves per row: nine planes x 2 * threads pixels
+    CUtensorMap tm_gs = tm_pk;
+    if (iterations > 1) {
+        const int rc = make_tensor_map(&tm_gs, a.gstat, a.wp, a.h, (size_t)a.n * 9, NTA, 9);
         if (rc != RF_OK) return rc;
     }
     dim3 pgrid((a.wp + 255) / 256, (a.h + PACK_ROWS - 1) / PACK_ROWS, a.n);
@@ -1154,11 +1181,11 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
         const bool last = it == iterations - 1;
         if (it == 0) {
             if (iterations > 1)
-                pass_a_kernel<SC, C, FULL_STORE><<<grid_a, NTA, smem_a, st>>>(tm_pk, a);
+                pass_a_kernel<SC, C, FULL_STORE><<<grid_a, NTA, smem_a, st>>>(tm_pk, tm_gs, a);
             else
-                pass_a_kernel<SC, C, FULL><<<grid_a, NTA, smem_a, st>>>(tm_pk, a);
+                pass_a_kernel<SC, C, FULL><<<grid_a, NTA, smem_a, st>>>(tm_pk, tm_gs, a);
         } else {
-            pass_a_kernel<SC, C, SRC_ONLY><<<grid_a, NTA, smem_s, st>>>(tm_pk, a);
+            pass_a_kernel<SC, C, SRC_ONLY><<<grid_a, NTA, smem_s, st>>>(tm_pk, tm_gs, a);
         }
         RF_LAUNCH_CHECK("gf2::pass_a_kernel");
         a.store_dst = last ? 1 : 0;
