@@ -63,7 +63,7 @@ struct Args {
     uint32_t *packed;      // [n][NP][h][wp]  NP = 1 (SC == 1: B,G,R,p) or 2 (SC == 3: B,G,R,0 / p0,p1,p2,0)
     float *ab;             // [n][SC][4][h][wp]  vertical prefix sums (restarted every seg_rows rows) of
                            // (a0, a1, a2, b), columns padded like `packed`
-    float *gstat;          // [n][9][h][wp]  guide statistics kept for iterated filtering: mean I (3) and the
+    float *gstat;          // [n][9][h][wg]  guide statistics kept for iterated filtering: mean I (3) and the
                            // inverse of cov(I) + eps*Id (00, 01, 02, 11, 12, 22); NULL when not wanted
     const int *plan;       // [h][PLAN_STRIDE]  row plan of pass B (plan_kernel)
     uint8_t *dst;          // [n][h][w][SC]
@@ -72,6 +72,7 @@ struct Args {
     int n, h, w, r;
     int rh;          // halo columns on each side: round_up(r + 1, 4)
     int wp;          // padded row pitch in pixels: round_up(w + 2 * rh + 16, 4)
+    int wg;          // row pitch of the statistics planes (no halo): round_up(w, 4)
     int twe;         // pass A: output columns per strip (multiple of 4)
     int seg_rows;    // pass A: output rows per CTA = rows per prefix segment
     int twe_b;       // pass B: output columns per strip (multiple of 4)
@@ -575,7 +576,8 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
     const int r = g.r;
     const int n_out = min(g.twe, g.w - sx0);  // <= 2 * NT: every thread solves at most one pixel pair per row
     const uint32_t bias = (uint32_t)(2 * r + 1) * 0x4B000000u;  // what the biased elements add to a window
-    float *GS = MODE == FULL ? nullptr : g.gstat + (size_t)img * 9 * plane;
+    const size_t gplane = (size_t)g.h * g.wg;
+    float *GS = MODE == FULL ? nullptr : g.gstat + (size_t)img * 9 * gplane;
     const f2 ia2 = dup2(g.inv_area);
 
     if (tid == 0) {
@@ -631,9 +633,9 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
             mi[2] = m[2];
             if (MODE == FULL_STORE) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) st_pair(GS + k * plane + row_off + g.rh + x, mi[k], both);
+                for (int k = 0; k < 3; ++k) st_pair(GS + k * gplane + (size_t)y * g.wg + x, mi[k], both);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) st_pair(GS + (3 + k) * plane + row_off + g.rh + x, inv[k], both);
+                for (int k = 0; k < 6; ++k) st_pair(GS + (3 + k) * gplane + (size_t)y * g.wg + x, inv[k], both);
             }
         }
 #pragma unroll
@@ -700,7 +702,7 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
                          : "memory");
             if (has_in) tma_load_3d(dst, &tmap, sx0 / 2, yin, img * NP, full);
             if (has_out) tma_load_3d(dst + ROW_BYTES, &tmap, sx0 / 2, yout, img * NP, full);
-            if (has_gs) tma_load_3d(dst + 2 * ROW_BYTES, &tmap_gs, (g.rh + sx0) / 2, y0 + t - 2 * r - 1, img * 9, full);
+            if (has_gs) tma_load_3d(dst + 2 * ROW_BYTES, &tmap_gs, sx0 / 2, y0 + t - 2 * r - 1, img * 9, full);
         }
     };
     auto release = [&](const int t) {
@@ -1151,7 +1153,7 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
     // cached statistics of the pixel pairs a CTA solves per row: nine planes x 2 * threads pixels
     CUtensorMap tm_gs = tm_pk;
     if (iterations > 1) {
-        const int rc = make_tensor_map(&tm_gs, a.gstat, a.wp, a.h, (size_t)a.n * 9, NTA, 9);
+        const int rc = make_tensor_map(&tm_gs, a.gstat, a.wg, a.h, (size_t)a.n * 9, NTA, 9);
         if (rc != RF_OK) return rc;
     }
     dim3 pgrid((a.wp + 255) / 256, (a.h + PACK_ROWS - 1) / PACK_ROWS, a.n);
@@ -1218,7 +1220,8 @@ static size_t plan_bytes(int h) { return ((size_t)h * PLAN_STRIDE * sizeof(int) 
 size_t workspace_per_image(int sc, int h, int w, int r, int iterations)
 {
     const size_t plane = (size_t)h * pitch(w, r);
-    return plane * 4 * (sc == 1 ? 1 : 2) + plane * 4 * 4 * sc + (iterations > 1 ? plane * 4 * 9 : 0) + plan_bytes(h);
+    const size_t gplane = (size_t)h * ((w + 3) & ~3);  // statistics planes carry no halo
+    return plane * 4 * (sc == 1 ? 1 : 2) + plane * 4 * 4 * sc + (iterations > 1 ? gplane * 4 * 9 : 0) + plan_bytes(h);
 }
 
 int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws, int n, int h, int w, int r,
@@ -1238,6 +1241,7 @@ int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws
     const Plan p = make_plan(sc, h, w, r);
     a.rh = p.rh;
     a.wp = p.wp;
+    a.wg = (w + 3) & ~3;
     a.twe = p.twe;
     a.twe_b = p.twe_b;
     a.seg_rows = h;
@@ -1247,7 +1251,7 @@ int run(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, void *ws
     a.packed = (uint32_t *)ws;
     a.ab = (float *)((uint32_t *)ws + (size_t)n * (sc == 1 ? 1 : 2) * plane);
     a.gstat = iterations > 1 ? a.ab + (size_t)n * sc * 4 * plane : nullptr;
-    a.plan = (const int *)(a.ab + (size_t)n * sc * 4 * plane + (iterations > 1 ? (size_t)n * 9 * plane : 0));
+    a.plan = (const int *)(a.ab + (size_t)n * sc * 4 * plane + (iterations > 1 ? (size_t)n * 9 * h * a.wg : 0));
 #define RF_GF2_LAUNCH(SC_)                                            \
     switch (p.C) {                                                    \
         case 8: return launch<SC_, 8>(a, p, iterations, st);          \
