@@ -251,11 +251,12 @@ static std::vector<TableEntry> g_tabs;
 //   A[ady][i] = (dx^2 + ady^2) * 0.5 / sigma_space^2 * log2(e), dx = i - rpad - 7, +inf outside the disc
 //   B[ady][i] = A[ady][i + 1]   (so that any two adjacent entries are an aligned register pair in A or in B)
 // followed by ceil4(half width) per |dy|.  The weight of a tap is exp2(-(alpha*ksqrt)^2 - A).
+// Call with g_tab_mu held, and keep it until the kernel that reads the table is in the stream: an eviction cudaFree()s
+// (which waits for running kernels) and must not hit a table between another thread's lookup and its launch.
 static int get_table(double sigma_space, const Geometry &g, const float **out)
 {
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_tab_mu);
     for (const TableEntry &e : g_tabs)
         if (e.device == dev && e.sigma_space == sigma_space && e.r == g.r) {
             *out = e.d_tab;
@@ -411,8 +412,6 @@ extern "C" int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t
     a.rpad = g.rpad;
     a.pitch = g.pitch;
     a.tabw = g.tabw;
-    int rc = bf::get_table(sigma_space, g, &a.tab);
-    if (rc != RF_OK) return rc;
     const bool sep = joint != src;
     cudaStream_t st = (cudaStream_t)stream;
     const double ksq = std::sqrt(0.5 / (sigma_color * sigma_color) * 1.4426950408889634074);
@@ -424,6 +423,13 @@ extern "C" int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t
         a.ksqrt = (float)ksq;
         const int wy = bf::pick_wy(a, g, sep);
         const size_t smem = bf::smem_bytes(wy, g, sep);
+        if (smem > 227 * 1024)
+            return fail(RF_EUNSUPPORTED,
+                        "rf_joint_bilateral_u8: radius %d with %s needs %zu bytes of shared memory (limit 232448)", g.r,
+                        sep ? "a distinct joint image" : "joint == src", smem);
+        std::lock_guard<std::mutex> lk(bf::g_tab_mu);  // held until the kernel that reads the table is in the stream
+        const int rc = bf::get_table(sigma_space, g, &a.tab);
+        if (rc != RF_OK) return rc;
 #define RF_BF_COLOR(WY)                                                                                  \
     case WY:                                                                                             \
         return sep ? bf::launch(bf::bf_color_kernel<WY, true>, WY, a, smem, st, "bf_color_kernel")       \

@@ -235,11 +235,12 @@ static std::vector<TableEntry> g_tabs;
 // tab[ady][t] = (E(qb), E(qb-1), E(qb+1), E(qb)) with qb = 2t - rpad and
 // E(dx) = (dx^2 + ady^2) * 0.5 / sigma_space^2 * log2(e) inside the disc, +inf outside;
 // followed by the even-rounded half width of every row.
+// Call with g_mu held; the caller keeps it until its kernel is in the stream: an eviction cudaFree()s (which waits for
+// running kernels) and must not hit a table between another thread's lookup and its launch.
 static int get_table(double sigma_space, const Geometry &g, const float **out)
 {
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_mu);
     for (const TableEntry &e : g_tabs)
         if (e.device == dev && e.sigma_space == sigma_space && e.r == g.r) {
             *out = e.d_tab;
@@ -302,12 +303,15 @@ static int poly_every()
 template <int WY, bool SEP, int POLY>
 static int launch(const Args &a, size_t smem, cudaStream_t st)
 {
-    static bool configured[64] = {};
+    static DeviceOnce once;  // one-time per-device kernel attribute; safe from several host threads
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(bf_gray2_kernel<WY, SEP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured[dev & 63] = true;
+    {
+        std::lock_guard<std::mutex> lock(once.mu);
+        if (!once.done[dev & 63]) {
+            RF_CUDA_TRY(cudaFuncSetAttribute(bf_gray2_kernel<WY, SEP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            once.done[dev & 63] = true;
+        }
     }
     dim3 grid((a.w + TW - 1) / TW, (a.h + WY - 1) / WY, a.n);
     bf_gray2_kernel<WY, SEP, POLY><<<grid, 32 * WY, smem, st>>>(a);
@@ -332,8 +336,6 @@ int run(const uint8_t *joint, const uint8_t *src, uint8_t *dst, int n, int h, in
     a.pitch = g.pitch;
     a.nchunk = g.nchunk;
     a.ksqrt = (float)(std::sqrt(0.5 / (sigma_color * sigma_color) * 1.4426950408889634074) * alpha_scale);
-    int rc = get_table(sigma_space, g, &a.tab);
-    if (rc != RF_OK) return rc;
     const bool sep = joint != src;
     // rows per CTA: big tiles amortise the window fill, small ones balance small grids over the SMs
     const long tiles16 = (long)((w + TW - 1) / TW) * ((h + 15) / 16) * n;
@@ -343,6 +345,9 @@ int run(const uint8_t *joint, const uint8_t *src, uint8_t *dst, int n, int h, in
     while (wy > 4 && smem_bytes(wy, g, sep) > 100 * 1024) wy >>= 1;
     const size_t smem = smem_bytes(wy, g, sep);
     if (smem > 227 * 1024) return fail(RF_EUNSUPPORTED, "bf_gray2: radius %d needs %zu bytes of shared memory", r, smem);
+    std::lock_guard<std::mutex> lk(g_mu);  // held until the kernel that reads the table is in the stream
+    const int rc = get_table(sigma_space, g, &a.tab);
+    if (rc != RF_OK) return rc;
 #define RF_BF2P(WY, PL) (sep ? launch<WY, true, PL>(a, smem, st) : launch<WY, false, PL>(a, smem, st))
 #define RF_BF2(WY)                                                                            \
     case WY:                                                                                  \

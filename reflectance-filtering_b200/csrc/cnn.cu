@@ -151,10 +151,13 @@ static int launch(const rf_cnn *net, const uint8_t *bgr, size_t n_px, float *out
                   cudaStream_t st)
 {
     const size_t smem = (256 + (size_t)net->n_params) * sizeof(float);
-    static bool configured[64] = {};
-    if (!configured[net->device & 63]) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(mlp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured[net->device & 63] = true;
+    static DeviceOnce once;
+    {
+        std::lock_guard<std::mutex> lock(once.mu);
+        if (!once.done[net->device & 63]) {
+            RF_CUDA_TRY(cudaFuncSetAttribute(mlp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            once.done[net->device & 63] = true;
+        }
     }
     const size_t n_pairs = (n_px + 1) / 2;
     size_t blocks = (n_pairs + THREADS - 1) / THREADS;

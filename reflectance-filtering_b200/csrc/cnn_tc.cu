@@ -387,18 +387,19 @@ int launch(const float *d_params, int n_hidden, const float *d_lut, const uint8_
 {
     const Smem sm = smem_map(n_hidden);
     const size_t smem = (size_t)sm.total + 1024;  // slack for the 1024-byte alignment of the base
-    static bool configured[64] = {};
-    static int occ[64] = {};
+    static DeviceOnce once;
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        // one CTA per SM: it allocates all 512 tensor-memory columns for its WGS pipelines
-        occ[dev & 63] = 1;
-        configured[dev & 63] = true;
+    {
+        std::lock_guard<std::mutex> lock(once.mu);
+        if (!once.done[dev & 63]) {
+            RF_CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            once.done[dev & 63] = true;
+        }
     }
     const size_t n_tiles = (n_px + TILE_M - 1) / TILE_M;
-    size_t blocks = (size_t)sm_count() * occ[dev & 63];
+    // one CTA per SM: it allocates all 512 tensor-memory columns for its WGS pipelines
+    size_t blocks = (size_t)sm_count();
     if (blocks > (n_tiles + WGS - 1) / WGS) blocks = (n_tiles + WGS - 1) / WGS;
     mlp_tc_kernel<<<(unsigned)blocks, THREADS, smem, st>>>(d_params, n_hidden, d_lut, bgr, n_px, out_f32, out_u8);
     RF_LAUNCH_CHECK("mlp_tc_kernel");

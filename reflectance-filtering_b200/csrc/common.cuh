@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 
@@ -34,6 +35,13 @@ extern std::atomic<unsigned long long> g_launches;
     } while (0)
 
 int sm_count();  // of the current device (cached per device)
+
+// One-time per-device setup (cudaFuncSetAttribute ...) that several host threads may reach at once:
+//   static DeviceOnce once;  std::lock_guard<std::mutex> lock(once.mu);  if (!once.done[dev & 63]) { ...; once.done[dev & 63] = true; }
+struct DeviceOnce {
+    std::mutex mu;
+    bool done[64] = {};
+};
 
 // ---- borders (OpenCV borderInterpolate) ---------------------------------------------------
 // REFLECT_101: gfedcb|abcdefgh|gfedcba      (joint bilateral)

@@ -6,8 +6,9 @@
 // the 0..255 scale, per-pixel 3x3 inverse by cofactors, q = mean(a).I + mean(b), round-half-even.
 //
 // Two streaming passes (DESIGN.md "K4"):
-//   pass A  reads guide + src (u8), forms the 9 + 4*SC window sums I, I*I', p, p*I as EXACT uint32
-//           integers (products <= 65,025, window <= 481^2 => < 2^32), converts each to the box
+//   pass A  reads guide + src (u8), forms the 9 + 4*SC window sums I, I*I', p, p*I as EXACT integers
+//           (products <= 65,025: a window of (2r+1)^2 <= 255^2 pixels stays below 2^32, so uint32 up to
+//           r = 127 and uint64 above), converts each to the box
 //           mean exactly as OpenCV does -- float(double(sum) * (1.0 / (2r+1)^2)) -- and solves
 //           for (a0, a1, a2, b) per source channel; writes one float4 per pixel per channel.
 //   pass B  box-means the four coefficient planes with FP64 running sums (OpenCV's box filter
@@ -117,13 +118,16 @@ struct PixA {
     }
 };
 
-template <int SC, int GC>
+// ST: type of the window sums (uint32_t for r <= MAX_RADIUS_U32, where 65,025 * (2r+1)^2 < 2^32; else 64-bit)
+constexpr int MAX_RADIUS_U32 = 127;
+
+template <int SC, int GC, typename ST>
 __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
 {
     constexpr int Q = n_quant<GC>(SC);
-    extern __shared__ __align__(16) uint32_t sm_u32[];
-    uint32_t *pref = sm_u32;              // [Q][NT + 1]
-    uint32_t *wtot = pref + Q * (NT + 1); // [Q][NW]
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    ST *pref = reinterpret_cast<ST *>(sm_raw);  // [Q][NT + 1]
+    ST *wtot = pref + Q * (NT + 1);             // [Q][NW]
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
     const int sx0 = blockIdx.x * g.twa;
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
 
     for (int q = tid; q < Q; q += NT) pref[q * (NT + 1)] = 0u;
 
-    uint32_t V[Q];
+    ST V[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) V[q] = 0u;
     if (col_active) {
@@ -160,15 +164,15 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
 #pragma unroll
             for (int q = 0; q < Q; ++q) V[q] += px.f[q];
         }
-        uint32_t Pq[Q];
+        ST Pq[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) Pq[q] = V[q];
-        block_scan_to_smem<uint32_t, Q>(Pq, pref, wtot);
+        block_scan_to_smem<ST, Q>(Pq, pref, wtot);
         if (is_out) {
             float m[Q];
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const uint32_t s = pref[q * (NT + 1) + tid + r + 1] - pref[q * (NT + 1) + tid - r];
+                const ST s = pref[q * (NT + 1) + tid + r + 1] - pref[q * (NT + 1) + tid - r];
                 m[q] = (float)((double)s * g.scale);  // == cv::boxFilter's float(sum * scale)
             }
             if constexpr (GC == 1) {
@@ -309,15 +313,20 @@ static size_t per_image_ws(int sc, int h, int w) { return (size_t)sc * h * w * s
 template <int SC, int GC>
 static int run(Args a, cudaStream_t st)
 {
-    const size_t smem_a = ((size_t)n_quant<GC>(SC) * (NT + 1 + NW)) * sizeof(uint32_t);
+    const bool wide = a.r > MAX_RADIUS_U32;  // 64-bit window sums
+    const size_t smem_a = ((size_t)n_quant<GC>(SC) * (NT + 1 + NW)) * (wide ? sizeof(unsigned long long) : sizeof(uint32_t));
     const size_t smem_b = ((size_t)(4 * SC) * (NT + 1 + NW)) * sizeof(double);
-    static bool configured[64] = {};
+    static DeviceOnce once;
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_b<SC, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured[dev & 63] = true;
+    {
+        std::lock_guard<std::mutex> lock(once.mu);
+        if (!once.done[dev & 63]) {
+            RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC, GC, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC, GC, unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_b<SC, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            once.done[dev & 63] = true;
+        }
     }
     const int max_twa = NT - 2 * a.r;
     const int strips = (a.w + max_twa - 1) / max_twa;
@@ -333,7 +342,10 @@ static int run(Args a, cudaStream_t st)
     }
     a.seg_rows = (a.h + segs - 1) / segs;
     dim3 grid(strips, (a.h + a.seg_rows - 1) / a.seg_rows, a.n);
-    gf_pass_a<SC, GC><<<grid, NT, smem_a, st>>>(a);
+    if (wide)
+        gf_pass_a<SC, GC, unsigned long long><<<grid, NT, smem_a, st>>>(a);
+    else
+        gf_pass_a<SC, GC, uint32_t><<<grid, NT, smem_a, st>>>(a);
     RF_LAUNCH_CHECK("gf_pass_a");
     gf_pass_b<SC, GC><<<grid, NT, smem_b, st>>>(a);
     RF_LAUNCH_CHECK("gf_pass_b");

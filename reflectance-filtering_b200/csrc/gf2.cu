@@ -1092,12 +1092,6 @@ static int make_tensor_map(CUtensorMap *tm, void *base, int wp, int h, size_t pl
     return RF_OK;
 }
 
-// one-time per-device kernel attributes; safe from several host threads
-struct DeviceOnce {
-    std::mutex mu;
-    bool done[64] = {};
-};
-
 template <int SC, int CB, int RB, int NS>
 static int launch_b(const Args &a, const Plan &p, cudaStream_t st)
 {

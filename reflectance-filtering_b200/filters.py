@@ -10,6 +10,7 @@ through the C ABI.  The ``*_device`` functions are the batched entry points
 """
 from __future__ import division, print_function
 
+import collections
 import ctypes as C
 import os
 
@@ -65,18 +66,28 @@ def joint_bilateral_device(joint: torch.Tensor, src: torch.Tensor, sigma_color: 
     return out
 
 
-_ws_cache = {}
+_ws_cache = collections.OrderedDict()
+_WS_CACHE_MAX = 8   # (device, stream) pairs whose scratch buffer is kept; least recently used goes first
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Scratch buffer of the current (device, stream): kernels of one stream run in order, so one buffer per
+    stream is never shared by two calls in flight.  Streams come and go (their handles are reused), so the cache
+    is a small LRU rather than a map that only grows."""
     key = (device.index, torch.cuda.current_stream().cuda_stream)
-    ws = _ws_cache.get(key)
+    ws = _ws_cache.pop(key, None)
     if ws is None or ws.numel() < nbytes:
-        ws = None
-        _ws_cache.pop(key, None)
+        ws = None   # release the smaller buffer before asking for the larger one
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
+    _ws_cache[key] = ws
+    while len(_ws_cache) > _WS_CACHE_MAX:
+        _ws_cache.popitem(last=False)
     return ws
+
+
+def release_workspaces() -> None:
+    """Drop every cached guided-filter scratch buffer (they are re-allocated on demand)."""
+    _ws_cache.clear()
 
 
 def guided_device(guide: torch.Tensor, src: torch.Tensor, radius: int, eps: float,
@@ -93,8 +104,18 @@ def guided_device(guide: torch.Tensor, src: torch.Tensor, radius: int, eps: floa
     if (ng, hg, wg) != (n, h, w):
         raise ValueError("guide and src must have the same batch and spatial size, got %r and %r"
                          % (tuple(guide.shape), tuple(src.shape)))
+    if guide.device != src.device:
+        raise ValueError("guide and src live on different devices")
     if out is None:
         out = torch.empty_like(src)
+    else:
+        dev.check_u8_cuda(out, "out")
+        if out.shape != src.shape or out.device != src.device:
+            raise ValueError("out must have the shape and device of src")
+    if workspace is not None:
+        if not (isinstance(workspace, torch.Tensor) and workspace.is_cuda and workspace.dtype == torch.uint8
+                and workspace.is_contiguous() and workspace.device == src.device):
+            raise ValueError("workspace must be a contiguous uint8 CUDA tensor on the device of src")
     L = _native.lib()
     with torch.cuda.device(src.device):
         dev.bind_device(src.device)

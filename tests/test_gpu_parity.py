@@ -262,6 +262,22 @@ def test_gf_ignores_workspace_contents(h, w, r, sc):
         assert mx <= 1 and frac < 2e-3, (fill, mx, frac)
 
 
+@pytest.mark.parametrize("r", [127, 128, 150, 240])
+def test_gf_large_radius_bright_image(r):
+    """Window sums of I*I' on a bright image exceed 2^32 from r = 128 on (65,025 * 257^2): the generic kernels switch
+    to 64-bit sums there (uint32 sums silently wrapped).  Bit-equal to the oracle on both sides."""
+    h, w = 2 * r + 40, 300
+    rng = np.random.default_rng(r)
+    gd = (255 - rng.integers(0, 6, size=(h, w, 3))).astype(np.uint8)       # saturated guide with a little texture
+    src = (250 - rng.integers(0, 40, size=(h, w))).astype(np.uint8)
+    out = filters.guided_device(dev_u8(gd[None]), dev_u8(src[None]), r, 3.0).cpu().numpy()[0]
+    ref = oracle.guided(gd, src, r, 3.0)
+    mx, frac = lsb_stats(out, ref)
+    assert mx <= 1 and frac < 2e-3, (r, mx, frac)
+    from reflectance_filtering_b200 import _native
+    assert _native.lib().rf_guided_max_radius() >= 240
+
+
 def test_gf_iterated_equals_repeated_calls():
     """rf_guided_iterated_u8 (guide statistics cached, output fed back through the packed planes) must be
     byte-identical to calling rf_guided_u8 on its own output -- fast path, generic path, gray and colour."""
