@@ -17,6 +17,10 @@ path).  Inputs rotate through a pool larger than L2 so no step re-reads cached i
 `cpu_baseline`: the reference-equivalent CPU path (cv2.dnn on the real prototxt/caffemodel +
             cv2.bilateralFilter, bit-identical to the restated jointBilateralFilter_8u) on a
             bounded sample, all host threads.
+Secondary objects of the same JSON line (rank 0; skipped with --no-extra): `config3_cnn_gf_x3` (device resident and
+through host buffers), `config4_strong` (a FIXED global batch of 1024x768 images split over the ranks: strong
+scaling), `config5_slice` (4K images: BF c15 s28 and GF c3 s45), `single_image` (configs[0]/[1] latency),
+`roofline_cnn`, `roofline_bf_color`, `parity`.
 """
 from __future__ import annotations
 
@@ -41,14 +45,22 @@ METRIC = "megapixels/sec end-to-end CNN->BF(CNN,CNN) c20 s22 (device-resident ui
 L2_BYTES = 126 * 1024 * 1024
 
 
-def make_config(batch, world, taps=3409, extra=None):
-    cfg = {"workload": "configs[1]: 512x384 CNN -> trunc u8 -> BF(CNN,CNN) c20 s22 (r=33, %d taps/px)" % taps,
-           "images_per_step_per_gpu": batch, "height": H, "width": W, "sigma_color": SIGMA_COLOR,
-           "sigma_spatial": SIGMA_SPATIAL,
-           "parallelism": "dp%d, contiguous image shards, no collective" % world}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def make_config(batch, world):
+    """The same dict from both arms (the driver compares them); everything arm-specific is a top-level key."""
+    return {"workload": "configs[1]: 512x384 CNN -> trunc u8 -> BF(CNN,CNN) c20 s22 (r=33, 3409 taps/px)",
+            "images_per_step_per_gpu": batch, "height": H, "width": W, "sigma_color": SIGMA_COLOR,
+            "sigma_spatial": SIGMA_SPATIAL,
+            "parallelism": "dp%d, contiguous image shards, no collective" % world}
+
+
+# What the parity claims of this repo rest on (oracle/README.md, DESIGN.md section 4): printed with every record so
+# that no reader takes "+-1 LSB against our restatement" for "+-1 LSB against OpenCV-contrib".
+PARITY = {
+    "cnn": "max abs error < 1e-5 vs cv2.dnn on the reference prototxt + caffemodel (tolerance 1e-3)",
+    "bf": "+-1 LSB vs a restatement that is bit-equal to cv2.bilateralFilter (joint == src) on every test image",
+    "gf": "unpinned vs ximgproc: +-1 LSB vs two independent in-house restatements of guided_filter.cpp and within "
+          "2 LSB of a float64 He-et-al. formulation; no cv2.ximgproc build exists offline to pin against",
+}
 
 
 def measured_peaks():
@@ -210,9 +222,9 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": mps, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": make_config(args.batch, max(1, args.gpus),
-                              extra={"reference_sample": "each step times %d image(s) of this workload on the host "
-                                                         "CPU (bounded sample)" % n_img}),
+        "config": make_config(args.batch, max(1, args.gpus)),
+        "reference_sample": "each step times %d image(s) of this workload on the host CPU (bounded sample)" % n_img,
+        "parity": PARITY,
         "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
                          "sample": "%d step(s) x %d image(s) of 512x384: cv2.dnn forward on the reference "
                                    "prototxt+caffemodel, trunc, cv2.bilateralFilter c20 s22; cv2 threads=%d"
@@ -221,6 +233,213 @@ def run_reference(args, rank: int):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------
+# secondary measurements of the CUDA arm (the other BASELINE.json configs, at bench-sized slices)
+# ---------------------------------------------------------------------------------------------
+# Per-launch DRAM traffic and executed instructions of the kernels below come from committed `ncu --set full`
+# captures, not from this run: every such number carries the file it was read from.
+NCU = {
+    "bf_gray2": {"dram_bytes": 12633600, "source": "profiles/r01_bf_gray2_ncu_full.txt (64 x 512x384)"},
+    "gf_x3": {"dram_bytes": None, "warp_instructions": None, "source": None},   # filled from profiles/r02_gf_final_ncu_full.txt
+}
+
+
+def timed(fn, reps, barrier, max_over_ranks):
+    """Mean device time of `fn` over `reps` back-to-back calls (CUDA events, max over ranks), after one warm-up."""
+    import torch
+    fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)) / reps
+
+
+def rolled_pool(gen, n, h, w, seed, device, distinct=8):
+    """`n` images from `distinct` seeded generator calls, decorrelated by rolls (generation is host-bound)."""
+    import torch
+    base = [gen(h, w, seed + i) for i in range(min(n, distinct))]
+    arr = np.stack([np.roll(base[i % len(base)], shift=11 * (i // len(base)), axis=1) for i in range(n)])
+    return torch.from_numpy(arr).to(device)
+
+
+def measure_extras(args, rank, world, device, pipe, dev_pool, host_pool, barrier, max_over_ranks):
+    import torch
+    from reflectance_filtering_b200 import filters, pipeline, synth
+    B = args.batch
+    reps = max(3, args.steps // 4)
+    x = {}
+
+    # ---- configs[0] shape: 3-channel BF with a copy of the image as joint (the colour kernel), batch B ----------
+    jcopy = dev_pool[0].clone()
+    cout = torch.empty_like(jcopy)
+    x["bf_color_ms"] = timed(lambda: filters.joint_bilateral_device(jcopy, dev_pool[0], SIGMA_COLOR, SIGMA_SPATIAL, out=cout),
+                             reps, barrier, max_over_ranks)
+    x["bf_color_batch"] = B
+    del jcopy, cout
+
+    # ---- configs[2]: CNN -> GF(CNN, flat) c3 s45 x3, batch of 64 ------------------------------------------------
+    GB = args.gf_batch
+    d_flat = rolled_pool(synth.flat, GB, H, W, 1000 * 3 + 500 + rank * GB, device, distinct=16)
+    d_imgs = dev_pool[0][:GB] if GB <= B else dev_pool.reshape(-1, H, W, 3)[:GB]
+    x["gf_batch"] = GB
+    x["cnn_gf_x3_ms"] = timed(lambda: pipe.cnn_gf(d_imgs, d_flat, 3.0, 45.0, iterations=3), reps, barrier, max_over_ranks)
+    r8 = pipe.reflectance_u8(d_imgs)
+    tmp = torch.empty_like(r8)
+    x["gf_single_ms"] = timed(lambda: filters.guided_device(d_flat, r8, 45, 3.0, out=tmp), reps, barrier, max_over_ranks)
+    x["gf_x3_ms"] = timed(lambda: filters.guided_device(d_flat, r8, 45, 3.0, out=tmp, iterations=3), reps, barrier,
+                          max_over_ranks)
+    # the same through pinned host buffers (images AND guides go up, the gray result comes down)
+    h_img = host_pool[0][:GB] if GB <= B else host_pool.reshape(-1, H, W, 3)[:GB]
+    h_gd = torch.empty((GB, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    h_gd.copy_(d_flat)
+    h_out = torch.empty((GB, H, W), dtype=torch.uint8, pin_memory=True)
+    t_wall = [0.0]
+
+    def gf_host():
+        t0 = time.perf_counter()
+        pipe.run_host("cnn_gf", h_img, h_out, guides=h_gd, chunk=args.chunk, n_streams=4, sigma_color=3.0,
+                      sigma_spatial=45.0, iterations=3)
+        t_wall[0] += time.perf_counter() - t0
+
+    ev_ms = timed(gf_host, reps, barrier, max_over_ranks)
+    x["cnn_gf_x3_e2e_ms"] = max(ev_ms, max_over_ranks(t_wall[0] * 1e3 / (reps + 1)))
+    x["cnn_gf_x3_e2e_ok"] = bool(torch.equal(h_out.to(device), pipe.cnn_gf(d_imgs, d_flat, 3.0, 45.0, iterations=3)))
+    del d_flat, r8, tmp
+
+    # ---- configs[3] slice, STRONG scaling: a fixed global batch of 1024x768 images, contiguous shards -------------
+    G4, H4, W4 = args.cfg4_images, 768, 1024
+    lo, hi = pipeline.shard_range(G4, rank, world)
+    imgs4 = rolled_pool(synth.natural, hi - lo, H4, W4, 1000 * 4 + lo, device)
+    out4 = torch.empty((hi - lo, H4, W4), dtype=torch.uint8, device=device)
+    r84 = torch.empty_like(out4)
+    x["cfg4"] = {"global_images": G4, "per_rank": hi - lo,
+                 "ms": timed(lambda: pipe.cnn_bf(imgs4, SIGMA_COLOR, SIGMA_SPATIAL, out=out4, scratch=r84), 3, barrier,
+                             max_over_ranks)}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    pipe.reflectance_u8(imgs4, out=r84)
+    ev[1].record()
+    filters.joint_bilateral_device(r84, r84, SIGMA_COLOR, SIGMA_SPATIAL, gray_replicated=True, out=out4)
+    ev[2].record()
+    barrier()
+    x["cfg4"]["cnn_ms"], x["cfg4"]["bf_ms"] = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    del imgs4, out4, r84
+
+    # ---- configs[4] slice: 4K images, CNN -> BF c15 s28 and CNN -> GF c3 s45 (weak: args.cfg5_images per rank) ----
+    N5, H5, W5 = args.cfg5_images, 2160, 3840
+    imgs5 = rolled_pool(synth.natural, N5, H5, W5, 1000 * 5 + rank * N5, device, distinct=2)
+    flat5 = rolled_pool(synth.flat, N5, H5, W5, 1000 * 5 + 500 + rank * N5, device, distinct=2)
+    out5 = torch.empty((N5, H5, W5), dtype=torch.uint8, device=device)
+    r85 = torch.empty_like(out5)
+    c5 = {"images_per_rank": N5}
+    c5["cnn_bf_ms"] = timed(lambda: pipe.cnn_bf(imgs5, 15.0, 28.0, out=out5, scratch=r85), 2, barrier, max_over_ranks)
+    c5["bf_ms"] = timed(lambda: filters.joint_bilateral_device(r85, r85, 15.0, 28.0, gray_replicated=True, out=out5), 2,
+                        barrier, max_over_ranks)
+    c5["cnn_gf_ms"] = timed(lambda: pipe.cnn_gf(imgs5, flat5, 3.0, 45.0, iterations=1), 3, barrier, max_over_ranks)
+    c5["gf_ms"] = timed(lambda: filters.guided_device(flat5, r85, 45, 3.0, out=out5), 3, barrier, max_over_ranks)
+    x["cfg5"] = c5
+    del imgs5, flat5, out5, r85
+
+    # ---- single-image latency: configs[0] (colour BF, joint = copy) and configs[1] (CNN -> BF(CNN,CNN)) ---------------
+    one = dev_pool[0][:1].contiguous()
+    jone = one.clone()
+    o3 = torch.empty_like(one)
+    o1 = torch.empty((1, H, W), dtype=torch.uint8, device=device)
+    s1 = torch.empty_like(o1)
+    x["single"] = {
+        "config0_bf_color_ms": timed(lambda: filters.joint_bilateral_device(jone, one, SIGMA_COLOR, SIGMA_SPATIAL, out=o3),
+                                     10, barrier, max_over_ranks),
+        "config1_cnn_bf_ms": timed(lambda: pipe.cnn_bf(one, SIGMA_COLOR, SIGMA_SPATIAL, out=o1, scratch=s1), 10, barrier,
+                                   max_over_ranks)}
+    return x
+
+
+def format_extras(x, world, peaks, peak_src, sms, f_max, taps):
+    """JSON objects of the secondary measurements (rank 0)."""
+    import ctypes as C
+    from reflectance_filtering_b200 import _native
+    out = {}
+    sfu_peak = sms * 16 * f_max
+    alu_peak = sms * 128 * f_max
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    px = x["bf_color_batch"] * H * W
+    ctaps = float(px) * taps / (x["bf_color_ms"] * 1e-3)
+    out["roofline_bf_color"] = {
+        "kernel": "bf_color_kernel (configs[0] shape: 3-channel joint = copy of the 3-channel source), batch %d"
+                  % x["bf_color_batch"],
+        "bound": "fp32", "launch_ms": x["bf_color_ms"], "achieved": ctaps * 10 / 1e9, "peak": alu_peak / 1e9,
+        "unit": "G FP32 lane-ops/s (SURVEY 8d: 10 lane-ops + 1 exp per tap)", "frac": ctaps * 10 / alu_peak,
+        "sfu": {"achieved_Gtap_s": ctaps / 1e9, "peak_Gtap_s": sfu_peak / 1e9, "frac": ctaps / sfu_peak},
+        "traffic": None}
+
+    # configs[2].  Algorithmic bytes per pixel per iteration, 1-channel src (DESIGN.md K4; SURVEY 8d counts 44 with
+    # a 3-byte source read in both passes): pass A reads 3 (guide) + 1 (src) and writes 16 (a0,a1,a2,b); pass B reads
+    # 16 + 3 (guide) and writes 1  => 40 B/px
+    gpx = x["gf_batch"] * H * W
+    bpp = 40.0
+    ach = gpx * bpp * 3 / (x["gf_x3_ms"] * 1e-3) / 1e9
+    t_hbm_ms = gpx * bpp * 3 / (hbm * 1e9) * 1e3
+    roof = {"kernel": "rf_guided_iterated_u8, 3 iterations: gf2 pack + pass_a<full+stats> + pass_b, then "
+                      "2 x (pass_a<source only> + pass_b)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+            "frac": ach / hbm, "bytes_per_pixel_per_iteration": bpp, "launch_ms": x["gf_x3_ms"],
+            "single_iteration_call_ms": x["gf_single_ms"], "traffic": NCU["gf_x3"]["dram_bytes"],
+            "traffic_source": NCU["gf_x3"]["source"], "peak_source": peak_src}
+    if NCU["gf_x3"]["warp_instructions"] and x["gf_batch"] == 64:
+        # what also bounds the call: the executed warp instructions of its seven launches (ncu) at one instruction per
+        # scheduler and clock; the call cannot be faster than the slower of the two bounds
+        t_issue_ms = NCU["gf_x3"]["warp_instructions"] / (sms * 4 * f_max) * 1e3
+        roof["issue_bound"] = {"warp_instructions": NCU["gf_x3"]["warp_instructions"],
+                               "thread_instructions_per_pixel_per_iteration":
+                                   NCU["gf_x3"]["warp_instructions"] * 32.0 / (gpx * 3),
+                               "ms_at_full_issue_rate": t_issue_ms, "ms_at_hbm_peak": t_hbm_ms,
+                               "frac_vs_max_of_both": max(t_issue_ms, t_hbm_ms) / x["gf_x3_ms"],
+                               "source": NCU["gf_x3"]["source"]}
+    h2d, d2h = world * gpx * 6, world * gpx
+    out["config3_cnn_gf_x3"] = {
+        "workload": "configs[2]: %d x 512x384, CNN -> GF(CNN, flat guide) c3.0 s45.0 (r=45), 3 iterations, "
+                    "uint8 re-quantisation between iterations" % x["gf_batch"],
+        "value": world * gpx / (x["cnn_gf_x3_ms"] * 1e-3) / 1e6, "unit": "MP/s", "ms_per_step": x["cnn_gf_x3_ms"],
+        "e2e": {"value": world * gpx / (x["cnn_gf_x3_e2e_ms"] * 1e-3) / 1e6, "unit": "MP/s",
+                "ms_per_step": x["cnn_gf_x3_e2e_ms"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "host_link_GBs": (h2d + d2h) / world / (x["cnn_gf_x3_e2e_ms"] * 1e-3) / 1e9,
+                "api": "Pipeline.run_host('cnn_gf', pinned images + pinned guides -> pinned uint8[N,H,W])",
+                "matches_device_path": x["cnn_gf_x3_e2e_ok"],
+                "note": "7 bytes cross the host link per pixel: this path is bound by it, not by the kernels"},
+        "roofline": roof}
+
+    r_, t_ = C.c_int(), C.c_int()
+    c4 = x["cfg4"]
+    px4 = c4["global_images"] * 768 * 1024
+    out["config4_strong"] = {
+        "workload": "configs[3] slice: a FIXED global batch of %d images of 1024x768, CNN -> BF(CNN,CNN) c20 s22, contiguous "
+                    "shards over the ranks, no collective" % c4["global_images"],
+        "scaling": "strong", "value": px4 / (c4["ms"] * 1e-3) / 1e6, "unit": "MP/s", "ms": c4["ms"],
+        "images_on_rank0": c4["per_rank"],
+        "rank0_kernels_ms": {"mlp_tc_kernel": c4["cnn_ms"], "bf_gray2_kernel": c4["bf_ms"]},
+        "roofline": {"kernel": "bf_gray2_kernel", "bound": "sfu",
+                     "frac": c4["per_rank"] * 768 * 1024 * float(taps) / (c4["bf_ms"] * 1e-3) / sfu_peak}}
+
+    _native.lib().rf_joint_bilateral_geometry(28.0, -1, C.byref(r_), C.byref(t_))
+    c5 = x["cfg5"]
+    px5 = c5["images_per_rank"] * 2160 * 3840
+    out["config5_slice"] = {
+        "workload": "configs[4] slice: %d image(s) of 3840x2160 per GPU" % c5["images_per_rank"], "scaling": "weak",
+        "cnn_bf_c15_s28": {"value": world * px5 / (c5["cnn_bf_ms"] * 1e-3) / 1e6, "unit": "MP/s", "ms": c5["cnn_bf_ms"],
+                           "taps_per_pixel": t_.value,
+                           "roofline": {"kernel": "bf_gray2_kernel", "bound": "sfu", "launch_ms": c5["bf_ms"],
+                                        "frac": px5 * float(t_.value) / (c5["bf_ms"] * 1e-3) / sfu_peak}},
+        "cnn_gf_c3_s45": {"value": world * px5 / (c5["cnn_gf_ms"] * 1e-3) / 1e6, "unit": "MP/s", "ms": c5["cnn_gf_ms"],
+                          "roofline": {"kernel": "rf_guided_u8 (gf2 pack + pass_a + pass_b)", "bound": "hbm",
+                                       "launch_ms": c5["gf_ms"], "achieved": px5 * 40.0 / (c5["gf_ms"] * 1e-3) / 1e9,
+                                       "peak": hbm, "unit": "GB/s", "frac": px5 * 40.0 / (c5["gf_ms"] * 1e-3) / 1e9 / hbm}}}
+    out["single_image"] = dict(x["single"], note="one 512x384 image per call, device resident, mean of 10 back-to-back calls")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -333,59 +552,9 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     cnn_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bf_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
 
-    # ---- configs[0] shape: 3-channel BF with a copy of the image as joint (the colour kernel) ---------
-    bfc_ms = None
-    if not args.no_gf:
-        c_steps = max(3, args.steps // 4)
-        jcopy = dev_pool[0].clone()
-        cout = torch.empty_like(jcopy)
-        filters.joint_bilateral_device(jcopy, dev_pool[0], SIGMA_COLOR, SIGMA_SPATIAL, out=cout)
-        cev = [torch.cuda.Event(enable_timing=True) for _ in range(c_steps + 1)]
-        barrier()
-        cev[0].record()
-        for i in range(c_steps):
-            filters.joint_bilateral_device(jcopy, dev_pool[0], SIGMA_COLOR, SIGMA_SPATIAL, out=cout)
-            cev[i + 1].record()
-        barrier()
-        bfc_ms = float(np.mean([cev[i].elapsed_time(cev[i + 1]) for i in range(c_steps)]))
-        del jcopy, cout
-
-    # ---- configs[2]: CNN -> GF(CNN, flat) c3 s45 x3, batch of 64 (secondary line, same JSON) ----------
-    gf = None
-    if not args.no_gf:
-        GB = args.gf_batch
-        flat = np.stack([synth.flat(H, W, 1000 * 3 + 500 + rank * GB + i) for i in range(min(GB, 16))])
-        d_flat = torch.from_numpy(np.stack([flat[i % len(flat)] for i in range(GB)])).to(device)
-        d_imgs = dev_pool[0][:GB] if GB <= B else dev_pool.reshape(-1, H, W, 3)[:GB]
-        for _ in range(2):
-            pipe.cnn_gf(d_imgs, d_flat, 3.0, 45.0, iterations=3)
-        g_steps = max(3, args.steps // 4)
-        barrier()
-        e0.record()
-        for _ in range(g_steps):
-            pipe.cnn_gf(d_imgs, d_flat, 3.0, 45.0, iterations=3)
-        e1.record()
-        barrier()
-        gf_ms = max_over_ranks(e0.elapsed_time(e1)) / g_steps
-        r8 = pipe.reflectance_u8(d_imgs)
-        gev = [torch.cuda.Event(enable_timing=True) for _ in range(g_steps + 1)]
-        tmp = None
-        barrier()
-        gev[0].record()
-        for i in range(g_steps):
-            tmp = filters.guided_device(d_flat, r8, 45, 3.0, out=tmp)
-            gev[i + 1].record()
-        barrier()
-        gf_iter_ms = float(np.mean([gev[i].elapsed_time(gev[i + 1]) for i in range(g_steps)]))
-        # the three iterations as one call (rf_guided_iterated_u8: guide statistics computed once)
-        barrier()
-        gev[0].record()
-        for i in range(g_steps):
-            tmp = filters.guided_device(d_flat, r8, 45, 3.0, out=tmp, iterations=3)
-            gev[i + 1].record()
-        barrier()
-        gf_x3_ms = float(np.mean([gev[i].elapsed_time(gev[i + 1]) for i in range(g_steps)]))
-        gf = {"ms_per_step": gf_ms, "gf_iteration_ms": gf_iter_ms, "gf_x3_ms": gf_x3_ms, "batch": GB, "steps": g_steps}
+    extra = None
+    if not args.no_extra:
+        extra = measure_extras(args, rank, world, device, pipe, dev_pool, host_pool, barrier, max_over_ranks)
 
     if rank != 0:
         if world > 1:
@@ -412,10 +581,11 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         "fp32_lane_ops": {"per_tap": 4, "achieved_Gop_s": achieved_taps * 4 / 1e9, "peak_Gop_s": alu_peak / 1e9,
                           "frac": achieved_taps * 4 / alu_peak},
         "taps_per_pixel": taps, "launch_ms": bf_ms, "share_of_step": bf_ms / (bf_ms + cnn_ms),
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this batch size, from the committed
-        # `ncu --set full` capture profiles/r01_bf_gray2_ncu_full.txt (12.63 MB read, 0 B written: the output is
-        # still in L2 when the kernel ends); algorithmic bytes are 2 * px = 25.2 MB
-        "traffic": 12633600 if B == 64 else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this batch size, from a committed `ncu --set
+        # full` capture (12.63 MB read, 0 B written: the output is still in L2 when the kernel ends; algorithmic
+        # bytes are 2 * px = 25.2 MB) -- not measured in this run
+        "traffic": NCU["bf_gray2"]["dram_bytes"] if B == 64 else None,
+        "traffic_source": NCU["bf_gray2"]["source"],
         "peak_source": "SM count x unit width x %s clock" % peak_src,
     }
     cnn_flops = 8704.0 * px_step
@@ -441,8 +611,9 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": make_config(B, world, taps, extra={"cache": "inputs rotate through a %d-batch pool (%.0f MB > L2)"
-                                                                 % (n_pool, n_pool * batch_bytes / 1e6)}),
+        "config": make_config(B, world),
+        "cache": "inputs rotate through a %d-batch pool (%.0f MB > L2)" % (n_pool, n_pool * batch_bytes / 1e6),
+        "parity": PARITY,
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": world * batch_bytes,
                 "d2h_bytes_per_step": world * px_step, "ms_per_step": e2e_ms / args.steps,
                 "api": "Pipeline.run_host(pinned host uint8[N,H,W,3] -> pinned host uint8[N,H,W])",
@@ -455,33 +626,8 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     }
     line["step_ms"] = {"best": float(np.min(per_step)), "median": float(np.median(per_step)),
                        "note": "per-step CUDA-event marks on rank 0 inside the timed region"}
-    if bfc_ms is not None:
-        ctaps = float(px_step) * taps / (bfc_ms * 1e-3)
-        line["roofline_bf_color"] = {
-            "kernel": "bf_color_kernel (configs[0] shape: 3-channel joint = copy of the 3-channel source), batch %d" % B,
-            "bound": "fp32", "launch_ms": bfc_ms, "achieved": ctaps * 10 / 1e9, "peak": alu_peak / 1e9,
-            "unit": "G FP32 lane-ops/s (SURVEY 8d: 10 lane-ops + 1 exp per tap)", "frac": ctaps * 10 / alu_peak,
-            "sfu": {"achieved_Gtap_s": ctaps / 1e9, "peak_Gtap_s": sfu_peak / 1e9, "frac": ctaps / sfu_peak},
-            "traffic": None}
-    if gf is not None:
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
-        gpx = gf["batch"] * H * W
-        # algorithmic bytes per pixel per iteration, 1-channel src: pass A reads 3 (guide)
-        # + 1 (src) and writes 16 (a0,a1,a2,b); pass B reads 16 + 3 (guide) and writes 1  => 40 B/px
-        bpp = 40.0
-        ach = gpx * bpp * 3 / (gf["gf_x3_ms"] * 1e-3) / 1e9
-        line["config3_cnn_gf_x3"] = {
-            "workload": "configs[2]: %d x 512x384, CNN -> GF(CNN, flat guide) c3.0 s45.0 (r=45), 3 iterations, "
-                        "uint8 re-quantisation between iterations" % gf["batch"],
-            "value": world * gpx / (gf["ms_per_step"] * 1e-3) / 1e6, "unit": "MP/s", "ms_per_step": gf["ms_per_step"],
-            "roofline": {"kernel": "rf_guided_iterated_u8, 3 iterations: gf2 pack + pass_a<full+stats> + pass_b, then "
-                                   "2 x (pass_a<source only> + pass_b)", "bound": "hbm", "achieved": ach,
-                         "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "bytes_per_pixel_per_iteration": bpp,
-                         "launch_ms": gf["gf_x3_ms"], "single_iteration_call_ms": gf["gf_iteration_ms"],
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the seven launches at batch 64, from
-                         # profiles/r01_gf_v8_ncu_full.txt: pass A<full+stats> 765 MB, pass B 856 MB, 2 x (pass A<source
-                         # only> 807 MB + pass B 856 MB), pack ~0.11 GB (algorithmic: 3 x 40 B x 12.58 Mpx = 1.51 GB)
-                         "traffic": 5060000000 if gf["batch"] == 64 else None, "peak_source": peak_src}}
+    if extra is not None:
+        line.update(format_extras(extra, world, peaks, peak_src, sms, f_max, taps))
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -511,8 +657,11 @@ def main():
     ap.add_argument("--chunk", type=int, default=8, help="images per H2D/compute/D2H chunk in the e2e path")
     ap.add_argument("--cpu-images", type=int, default=6, help="sample size of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-gf", action="store_true", help="skip the secondary configs[2] (CNN->GF x3) measurement")
+    ap.add_argument("--no-extra", "--no-gf", dest="no_extra", action="store_true",
+                    help="skip the secondary measurements (configs[0], [2], [3], [4] slices, single-image latency)")
     ap.add_argument("--gf-batch", type=int, default=64)
+    ap.add_argument("--cfg4-images", type=int, default=128, help="global batch of the strong-scaling configs[3] slice")
+    ap.add_argument("--cfg5-images", type=int, default=2, help="4K images per GPU of the configs[4] slice")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

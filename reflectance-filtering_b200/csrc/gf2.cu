@@ -1124,7 +1124,6 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
     const size_t smem_a = pass_a_smem<SC, C, FULL>();
     const size_t smem_s = pass_a_smem<SC, C, SRC_ONLY>();
     static DeviceOnce once;
-    static int occ_a = 1;
     int dev = 0;
     RF_CUDA_TRY(cudaGetDevice(&dev));
     {
@@ -1133,8 +1132,6 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
             RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C, FULL_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             RF_CUDA_TRY(cudaFuncSetAttribute(pass_a_kernel<SC, C, SRC_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            RF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, pass_a_kernel<SC, C, FULL_STORE>, NTA, smem_a));
-            if (occ_a < 1) occ_a = 1;
             once.done[dev & 63] = true;
         }
     }
@@ -1153,21 +1150,15 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
     dim3 pgrid((a.wp + 255) / 256, (a.h + PACK_ROWS - 1) / PACK_ROWS, a.n);
     pack_kernel<SC><<<pgrid, 256, 0, st>>>(a);
     RF_LAUNCH_CHECK("gf2::pack_kernel");
-    // Row segments: the vertical sums make a column strictly sequential, so small batches are split into
-    // row segments (each pays 2r warm-up rows) until the grid fills ONE wave of resident CTAs -- measured:
-    // more than one wave loses to tail effects, fewer leaves SMs idle (profiles/r01_gf2_segments.txt).
-    // One segmentation for every iteration: the prefix rows pass A writes restart at segment boundaries, and the
-    // row plan of pass B is built for exactly that segmentation.
+    // Row segments: the vertical sums make a column strictly sequential, so the rows are split into segments of
+    // about 96 rows (each pays 2r warm-up rows; measured optimum for 64 x 512x384 and within 4 % of the best for
+    // 8 x 4K, profiles/r02_gf_segments.txt).  The segmentation depends on the image height ONLY: the prefix rows
+    // pass A writes restart at segment boundaries and their FP32 rounding depends on where they restart, so a
+    // segmentation chosen from the batch size would make the bytes of an image depend on how a batch is sharded
+    // or chunked.  One segmentation for every iteration: the row plan of pass B is built for exactly it.
     static const int force_a = env_int("RF_GF2_SEGS_A");
-    const long ctas = (long)p.strips * a.n;
-    int segs = force_a;
-    if (segs <= 0) {
-        const int max_segs = a.h / 64 > 1 ? a.h / 64 : 1;  // shortest segment: 64 rows
-        long s = (long)sm_count() * occ_a / ctas;
-        if (s < 1) s = 1;
-        if (s > max_segs) s = max_segs;
-        segs = (int)s;
-    }
+    int segs = force_a > 0 ? force_a : (a.h + 48) / 96;
+    if (segs < 1) segs = 1;
     a.seg_rows = (a.h + segs - 1) / segs;
     if (!plan_fits(a.h, a.r, a.seg_rows)) a.seg_rows = a.h;  // one segment: at most two terms per reflected copy
     const dim3 grid_a(p.strips, (a.h + a.seg_rows - 1) / a.seg_rows, a.n);

@@ -278,6 +278,20 @@ def test_gf_large_radius_bright_image(r):
     assert _native.lib().rf_guided_max_radius() >= 240
 
 
+def test_gf_bytes_do_not_depend_on_batch_composition():
+    """An image's output must be the same bytes whether it is filtered alone, in a chunk or in the whole batch
+    (sharded == unsharded).  The row segmentation of the fast path once depended on the batch size."""
+    n, h, w, r = 12, 200, 300, 20
+    gd = np.stack([synth.flat(h, w, 900 + i) for i in range(n)])
+    src = np.ascontiguousarray(np.stack([synth.natural(h, w, 950 + i) for i in range(n)])[..., 1])
+    dg, ds = dev_u8(gd), dev_u8(src)
+    for iters in (1, 3):
+        whole = filters.guided_device(dg, ds, r, 3.0, iterations=iters)
+        for lo, hi in ((0, 1), (1, 4), (4, 12)):
+            part = filters.guided_device(dg[lo:hi].contiguous(), ds[lo:hi].contiguous(), r, 3.0, iterations=iters)
+            assert torch.equal(part, whole[lo:hi]), (iters, lo, hi)
+
+
 def test_gf_iterated_equals_repeated_calls():
     """rf_guided_iterated_u8 (guide statistics cached, output fed back through the packed planes) must be
     byte-identical to calling rf_guided_u8 on its own output -- fast path, generic path, gray and colour."""
