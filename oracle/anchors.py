@@ -180,6 +180,47 @@ def guided_cv2box(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: fl
     return out if src_u8.ndim == 3 else out[:, :, 0]
 
 
+def _box_mean_f64(x: np.ndarray, r: int) -> np.ndarray:
+    """Mean over the (2r+1)^2 window with symmetric padding (edge pixel repeated: fedcba|abcdefgh|hgfedcb), float64,
+    by a summed-area table.  x: [H, W] or [H, W, K]."""
+    pad = [(r + 1, r), (r + 1, r)] + [(0, 0)] * (x.ndim - 2)
+    xp = np.pad(x.astype(np.float64), pad, mode="symmetric")
+    sat = xp.cumsum(axis=0).cumsum(axis=1)
+    k = 2 * r + 1
+    h, w = x.shape[:2]
+    tot = sat[k:k + h, k:k + w] - sat[:h, k:k + w] - sat[k:k + h, :w] + sat[:h, :w]
+    return tot / float(k * k)
+
+
+def guided_float64(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: float) -> np.ndarray:
+    """The guided filter as the paper states it (He, Sun, Tang, "Guided Image Filtering", eqs. 19-21 of the colour
+    case), entirely in float64: a_k = (Sigma_k + eps U)^-1 (mean(I p) - mu_k mean(p)) by np.linalg.solve,
+    b_k = mean(p) - a_k . mu_k, q = mean(a) . I + mean(b).  No OpenCV code path, no float32, no cofactors: a third,
+    structurally different formulation used as a BOUND on the restatements (they follow guided_filter.cpp's float32
+    arithmetic and may differ from this by rounding, not by more)."""
+    r = int(radius)
+    G = guide_u8.reshape(guide_u8.shape[0], guide_u8.shape[1], -1).astype(np.float64)
+    S = src_u8.reshape(src_u8.shape[0], src_u8.shape[1], -1).astype(np.float64)
+    gc = G.shape[2]
+    mu = _box_mean_f64(G, r)                                                   # [H, W, gc]
+    corr = _box_mean_f64(G[:, :, :, None] * G[:, :, None, :], r) if gc > 1 else None
+    if gc > 1:
+        corr = corr.reshape(G.shape[0], G.shape[1], gc, gc)
+        sigma = corr - mu[:, :, :, None] * mu[:, :, None, :] + eps * np.eye(gc)
+    else:
+        sigma = (_box_mean_f64(G[:, :, 0] ** 2, r) - mu[:, :, 0] ** 2 + eps)[:, :, None, None]
+    out = np.empty(S.shape, np.uint8)
+    for c in range(S.shape[2]):
+        p = S[:, :, c]
+        mp = _box_mean_f64(p, r)
+        cov_ip = _box_mean_f64(G * p[:, :, None], r) - mu * mp[:, :, None]     # [H, W, gc]
+        a = np.linalg.solve(sigma, cov_ip[:, :, :, None])[:, :, :, 0]
+        b = mp - (a * mu).sum(axis=2)
+        q = (_box_mean_f64(a, r) * G).sum(axis=2) + _box_mean_f64(b, r)
+        out[:, :, c] = np.clip(np.rint(q), 0, 255).astype(np.uint8)
+    return out.reshape(src_u8.shape)
+
+
 def quantize_like_imwrite(gray_f32: np.ndarray) -> np.ndarray:
     """image_utils.py:60-73 for the CNN output: normalize is a no-op (sigmoid < 1), then
     ``(image * 255).astype(np.uint8)``; cv2.imread of the 1-channel PNG replicates it to
