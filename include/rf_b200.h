@@ -86,12 +86,35 @@ int rf_cnn_forward_u8(const rf_cnn *net, const uint8_t *bgr, int n, int h, int w
  * exp(-alpha^2 / 2 sigma_color^2) with alpha = sum_c |J0_c - Jk_c|, output round-half-even.
  * sigma <= 0 is replaced by 1 as OpenCV does (the Python operator rejects it earlier).
  * joint may alias src (self-guided); dst must not alias either.
- * RF_EUNSUPPORTED if the radius exceeds rf_joint_bilateral_max_radius(). */
+ * Radii up to rf_joint_bilateral_fast_max_radius() run on the shared-memory-tiled kernels; larger ones (up to
+ * rf_joint_bilateral_max_radius(), else RF_EUNSUPPORTED) on the generic kernel. */
 int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t *src, int sc, uint8_t *dst,
                           int n, int h, int w, double sigma_color, double sigma_space, int d,
                           unsigned flags, void *stream);
+
+/* The rest of cv2.ximgproc.jointBilateralFilter(joint, src, d, sigmaColor, sigmaSpace[, dst[, borderType]])
+ * (the call site filter_reflectance.py:60-64 passes whatever ndarrays it is given):
+ * border_type = OpenCV's cv::BorderTypes value as copyMakeBorder applies it to joint and src (CONSTANT pads with 0). */
+#define RF_BORDER_CONSTANT 0
+#define RF_BORDER_REPLICATE 1
+#define RF_BORDER_REFLECT 2
+#define RF_BORDER_WRAP 3
+#define RF_BORDER_REFLECT_101 4 /* cv2.BORDER_DEFAULT, what rf_joint_bilateral_u8 uses */
+int rf_joint_bilateral_u8_border(const uint8_t *joint, int jc, const uint8_t *src, int sc, uint8_t *dst,
+                                 int n, int h, int w, double sigma_color, double sigma_space, int d,
+                                 unsigned flags, int border_type, void *stream);
+
+/* CV_32F images (jointBilateralFilter_32f): float joint [n][h][w][jc], src / dst [n][h][w][sc].  The range weight is
+ * interpolated in an exp table of 4096 * jc bins scaled to each joint image's own value range; the spatial part is
+ * as in the 8-bit version; no rounding of the output.  `workspace`: device scratch of at least
+ * rf_joint_bilateral_f32_workspace_bytes(n, jc) bytes (the per-image tables). */
+size_t rf_joint_bilateral_f32_workspace_bytes(int n, int jc);
+int rf_joint_bilateral_f32(const float *joint, int jc, const float *src, int sc, float *dst, int n, int h, int w,
+                           double sigma_color, double sigma_space, int d, int border_type, void *workspace,
+                           size_t workspace_bytes, void *stream);
 int rf_joint_bilateral_geometry(double sigma_space, int d, int *radius, int *taps);
 int rf_joint_bilateral_max_radius(void);
+int rf_joint_bilateral_fast_max_radius(void);
 
 /* ---- guided filter, 8-bit -------------------------------------------------------------------
  * guide [n][h][w][gc], gc in {3, 1}; src / dst [n][h][w][sc], sc in {1, 3}.  Semantics of ximgproc

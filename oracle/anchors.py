@@ -76,7 +76,7 @@ def bilateral_self(image_u8: np.ndarray, sigma_color: float, sigma_space: float)
 
 
 def joint_bilateral_numpy(joint_u8: np.ndarray, src_u8: np.ndarray, d: int, sigma_color: float,
-                          sigma_space: float) -> np.ndarray:
+                          sigma_space: float, border_type: int = 4) -> np.ndarray:
     """SURVEY A.2 (jointBilateralFilter_8u) written independently of oracle/rf_oracle.c: cv2.copyMakeBorder for the
     REFLECT_101 padding, numpy float32 arithmetic vectorised over the image, taps accumulated in the same raster
     order one at a time.  For joint != src, where cv2.bilateralFilter cannot serve as the anchor."""
@@ -89,7 +89,7 @@ def joint_bilateral_numpy(joint_u8: np.ndarray, src_u8: np.ndarray, d: int, sigm
     sigma_space = sigma_space if sigma_space > 0 else 1.0
     radius = max(int(np.rint(sigma_space * 1.5)) if d <= 0 else d // 2, 1)   # cvRound = round-half-even
     cw = np.exp(np.arange(256 * joint.shape[2], dtype=np.float64) ** 2 * (-0.5 / sigma_color ** 2)).astype(f32)
-    pad = lambda a: cv2.copyMakeBorder(a, radius, radius, radius, radius, cv2.BORDER_REFLECT_101).reshape(
+    pad = lambda a: cv2.copyMakeBorder(a, radius, radius, radius, radius, int(border_type), value=0).reshape(
         a.shape[0] + 2 * radius, a.shape[1] + 2 * radius, -1)
     pj, ps = pad(np.ascontiguousarray(joint)).astype(np.int32), pad(np.ascontiguousarray(src)).astype(f32)
     j0 = pj[radius:radius + h, radius:radius + w]
@@ -107,6 +107,47 @@ def joint_bilateral_numpy(joint_u8: np.ndarray, src_u8: np.ndarray, d: int, sigm
             wsum += wt
     out = np.clip(np.rint(acc / wsum[:, :, None]), 0, 255).astype(np.uint8)
     return out if src_u8.ndim == 3 else out[:, :, 0]
+
+
+def joint_bilateral_f32_numpy(joint: np.ndarray, src: np.ndarray, d: int, sigma_color: float, sigma_space: float,
+                              border_type: int = 4) -> np.ndarray:
+    """jointBilateralFilter_32f (SURVEY A.2 last bullet) written independently of oracle/rf_oracle.c: exp table of
+    4096 bins per joint channel over the joint image's value range, linear interpolation between bins,
+    cv2.copyMakeBorder padding, numpy float32 arithmetic, taps in raster order."""
+    _need_cv2()
+    f32 = np.float32
+    J = joint.reshape(joint.shape[0], joint.shape[1], -1).astype(f32)
+    S = src.reshape(src.shape[0], src.shape[1], -1).astype(f32)
+    h, w = S.shape[:2]
+    jc = J.shape[2]
+    radius = max(int(np.rint(sigma_space * 1.5)) if d <= 0 else d // 2, 1)
+    nbins = 4096 * jc
+    color_range = f32((float(J.max()) - float(J.min())) * jc)
+    scale = f32(nbins) / color_range
+    lut = np.exp((np.arange(nbins + 2, dtype=np.float64) / float(scale)) ** 2 * (-0.5 / sigma_color ** 2)).astype(f32)
+    pad = lambda a: cv2.copyMakeBorder(a, radius, radius, radius, radius, int(border_type), value=0).reshape(
+        a.shape[0] + 2 * radius, a.shape[1] + 2 * radius, -1)
+    pj, ps = pad(np.ascontiguousarray(J)), pad(np.ascontiguousarray(S))
+    j0 = pj[radius:radius + h, radius:radius + w]
+    acc = np.zeros((h, w, S.shape[2]), f32)
+    wsum = np.zeros((h, w), f32)
+    for i in range(-radius, radius + 1):
+        for j in range(-radius, radius + 1):
+            if i * i + j * j > radius * radius:
+                continue
+            sw = f32(np.exp((i * i + j * j) * (-0.5 / sigma_space ** 2)))
+            jk = pj[radius + i:radius + i + h, radius + j:radius + j + w]
+            alpha = np.zeros((h, w), f32)
+            for c in range(jc):
+                alpha = alpha + np.abs(j0[:, :, c] - jk[:, :, c])
+            alpha = alpha * scale
+            idx = np.minimum(alpha.astype(np.int32), nbins)
+            frac = alpha - idx.astype(f32)
+            wt = sw * (lut[idx] + frac * (lut[idx + 1] - lut[idx]))
+            acc += wt[:, :, None] * ps[radius + i:radius + i + h, radius + j:radius + j + w]
+            wsum += wt
+    out = acc / wsum[:, :, None]
+    return out.reshape(src.shape)
 
 
 def box_mean_cv2(plane_f32: np.ndarray, r: int) -> np.ndarray:

@@ -14,6 +14,8 @@
  *   orc_joint_bilateral_u8  cv2.ximgproc.jointBilateralFilter call at
  *                           filter_reflectance.py:60-64 (OpenCV-contrib 3.1.0
  *                           joint_bilateral_filter.cpp, jointBilateralFilter_8u, A.2)
+ *   orc_joint_bilateral_u8_border / orc_joint_bilateral_f32   the rest of that function's surface (borderType
+ *                           argument, CV_32F images: SURVEY 8f-4), not reachable from the reference CLI
  *   orc_box_mean_reflect    cv::boxFilter(CV_32F, normalize, BORDER_REFLECT) as used by
  *                           ximgproc's guided filter (A.3 step 2)
  *   orc_guided_u8           cv2.ximgproc.guidedFilter call at filter_reflectance.py:67-70
@@ -78,6 +80,24 @@ static int reflect(int p, int len)
         else p = 2 * len - 1 - p;
     }
     return p;
+}
+
+/* cv::borderInterpolate for the border types of copyMakeBorder: 0 CONSTANT (returns -1: the padded value is 0),
+ * 1 REPLICATE aaaaaa|abcdefgh|hhhhhhh, 2 REFLECT fedcba|abcdefgh|hgfedcb, 3 WRAP cdefgh|abcdefgh|abcdefg,
+ * 4 REFLECT_101 gfedcb|abcdefgh|gfedcba (BORDER_DEFAULT)                                                     */
+static int border_index(int p, int len, int border_type)
+{
+    if (p >= 0 && p < len) return p;
+    switch (border_type) {
+        case 0: return -1;
+        case 1: return p < 0 ? 0 : len - 1;
+        case 2: return reflect(p, len);
+        case 3: {
+            int q = p % len;
+            return q < 0 ? q + len : q;
+        }
+        default: return reflect101(p, len);
+    }
 }
 
 static uint8_t sat_u8(float v)
@@ -191,10 +211,11 @@ void orc_quantize_trunc(const float *x, long n, uint8_t *out)
 }
 
 /* ---- joint bilateral filter, 8-bit --------------------------------------- */
-int orc_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t *src, int sc, uint8_t *dst,
-                           int h, int w, double sigma_color, double sigma_space, int d)
+int orc_joint_bilateral_u8_border(const uint8_t *joint, int jc, const uint8_t *src, int sc, uint8_t *dst,
+                                  int h, int w, double sigma_color, double sigma_space, int d, int border_type)
 {
     if (!(jc == 1 || jc == 3) || !(sc == 1 || sc == 3) || h < 1 || w < 1) return ORC_EINVAL;
+    if (border_type < 0 || border_type > 4) return ORC_EINVAL;
     if (sigma_color <= 0) sigma_color = 1;
     if (sigma_space <= 0) sigma_space = 1;
     int radius = d <= 0 ? (int)lrint(sigma_space * 1.5) : d / 2;
@@ -225,13 +246,17 @@ int orc_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t *src, int
             oj[maxk] = j;
             ++maxk;
         }
-    /* copyMakeBorder(..., BORDER_REFLECT_101) of both images */
+    /* copyMakeBorder(..., borderType) of both images (the call site uses the default, BORDER_REFLECT_101;
+     * BORDER_CONSTANT pads with 0) */
     for (int y = 0; y < ph; ++y) {
-        const int sy = reflect101(y - radius, h);
+        const int sy = border_index(y - radius, h, border_type);
         for (int x = 0; x < pw; ++x) {
-            const int sx = reflect101(x - radius, w);
-            for (int c = 0; c < jc; ++c) pj[((size_t)y * pw + x) * jc + c] = joint[((size_t)sy * w + sx) * jc + c];
-            for (int c = 0; c < sc; ++c) ps[((size_t)y * pw + x) * sc + c] = src[((size_t)sy * w + sx) * sc + c];
+            const int sx = border_index(x - radius, w, border_type);
+            const int inside = sy >= 0 && sx >= 0;
+            for (int c = 0; c < jc; ++c)
+                pj[((size_t)y * pw + x) * jc + c] = inside ? joint[((size_t)sy * w + sx) * jc + c] : 0;
+            for (int c = 0; c < sc; ++c)
+                ps[((size_t)y * pw + x) * sc + c] = inside ? src[((size_t)sy * w + sx) * sc + c] : 0;
         }
     }
 #pragma omp parallel for schedule(dynamic, 4)
@@ -262,6 +287,102 @@ int orc_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t *src, int
         }
     }
     free(cw); free(sw); free(oi); free(oj); free(pj); free(ps);
+    return ORC_OK;
+}
+
+int orc_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t *src, int sc, uint8_t *dst,
+                           int h, int w, double sigma_color, double sigma_space, int d)
+{
+    return orc_joint_bilateral_u8_border(joint, jc, src, sc, dst, h, w, sigma_color, sigma_space, d, 4);
+}
+
+/* ---- joint bilateral filter, CV_32F (not reachable from the reference CLI; SURVEY A.2 last bullet, 8f-4) ------
+ * jointBilateralFilter_32f of joint_bilateral_filter.cpp [upstream, recollection], the structure of imgproc's
+ * bilateralFilter_32f, against which the joint == src case is pinned (tests/test_oracle_pins.py):
+ *   colorRange = (max - min over all joint values) * jc;  kExpNumBins = 4096 * jc;  scaleIndex = kExpNumBins / colorRange
+ *   expLUT[i] = (float)exp((i / scaleIndex)^2 * (-0.5 / sigmaColor^2)),  i = 0 .. kExpNumBins + 1
+ *   per tap: alpha = sum_c |J0_c - Jk_c| * scaleIndex; idx = (int)alpha; alpha -= idx;
+ *            w = spaceWeight[k] * (expLUT[idx] + alpha * (expLUT[idx+1] - expLUT[idx]));  dst = sum(w src) / sum(w)
+ * A constant joint image (max - min < FLT_EPSILON) makes every range weight 1: the spatial Gaussian over the disc
+ * (upstream switches to a square GaussianBlur there [recollection]; imgproc copies the source -- both unverifiable
+ * offline, so the degenerate case is defined by the formula itself and stated in DESIGN.md).                    */
+int orc_joint_bilateral_f32(const float *joint, int jc, const float *src, int sc, float *dst, int h, int w,
+                            double sigma_color, double sigma_space, int d, int border_type)
+{
+    if (!(jc == 1 || jc == 3) || !(sc == 1 || sc == 3) || h < 1 || w < 1) return ORC_EINVAL;
+    if (border_type < 0 || border_type > 4) return ORC_EINVAL;
+    if (sigma_color <= 0) sigma_color = 1;
+    if (sigma_space <= 0) sigma_space = 1;
+    int radius = d <= 0 ? (int)lrint(sigma_space * 1.5) : d / 2;
+    if (radius < 1) radius = 1;
+    const double gcc = -0.5 / (sigma_color * sigma_color);
+    const double gsc = -0.5 / (sigma_space * sigma_space);
+    float mn = joint[0], mx = joint[0];
+    for (size_t i = 0; i < (size_t)h * w * jc; ++i) {
+        if (joint[i] < mn) mn = joint[i];
+        if (joint[i] > mx) mx = joint[i];
+    }
+    const int flat = fabs((double)mx - (double)mn) < 1.1920928955078125e-7;
+    const int nbins = 4096 * jc;
+    const float color_range = (float)((double)mx - (double)mn) * jc;
+    const float scale_index = flat ? 0.0f : nbins / color_range;
+    const int side = 2 * radius + 1;
+    float *lut = (float *)malloc(sizeof(float) * (nbins + 2));
+    float *sw = (float *)malloc(sizeof(float) * side * side);
+    int *oi = (int *)malloc(sizeof(int) * side * side);
+    int *oj = (int *)malloc(sizeof(int) * side * side);
+    if (!lut || !sw || !oi || !oj) {
+        free(lut); free(sw); free(oi); free(oj);
+        return ORC_ENOMEM;
+    }
+    for (int i = 0; i < nbins + 2; ++i) {
+        const double val = flat ? 0.0 : i / (double)scale_index;
+        lut[i] = (float)exp(val * val * gcc);
+    }
+    int maxk = 0;
+    for (int i = -radius; i <= radius; ++i)
+        for (int j = -radius; j <= radius; ++j) {
+            double r = sqrt((double)i * i + (double)j * j);
+            if (r > radius) continue;
+            sw[maxk] = (float)exp(r * r * gsc);
+            oi[maxk] = i;
+            oj[maxk] = j;
+            ++maxk;
+        }
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < h; ++y) {
+        for (int x = 0; x < w; ++x) {
+            const float *j0 = joint + ((size_t)y * w + x) * jc;
+            float wsum = 0.0f, s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+            for (int k = 0; k < maxk; ++k) {
+                const int yy = border_index(y + oi[k], h, border_type), xx = border_index(x + oj[k], w, border_type);
+                const int inside = yy >= 0 && xx >= 0;
+                const float zero[3] = {0.0f, 0.0f, 0.0f};
+                const float *jk = inside ? joint + ((size_t)yy * w + xx) * jc : zero;
+                const float *sk = inside ? src + ((size_t)yy * w + xx) * sc : zero;
+                float alpha = 0.0f;
+                for (int c = 0; c < jc; ++c) alpha += fabsf(j0[c] - jk[c]);
+                alpha *= scale_index;
+                int idx = (int)alpha;
+                if (idx > nbins) idx = nbins;  /* a zero-padded border can exceed the image's own range */
+                alpha -= (float)idx;
+                const float wt = sw[k] * (lut[idx] + alpha * (lut[idx + 1] - lut[idx]));
+                s0 += wt * sk[0];
+                if (sc == 3) {
+                    s1 += wt * sk[1];
+                    s2 += wt * sk[2];
+                }
+                wsum += wt;
+            }
+            float *o = dst + ((size_t)y * w + x) * sc;
+            o[0] = s0 / wsum;
+            if (sc == 3) {
+                o[1] = s1 / wsum;
+                o[2] = s2 / wsum;
+            }
+        }
+    }
+    free(lut); free(sw); free(oi); free(oj);
     return ORC_OK;
 }
 

@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "librf_b200.so")
 
 RF_OK, RF_EINVAL, RF_EUNSUPPORTED, RF_ECUDA, RF_ENOMEM = 0, 1, 2, 3, 4
 RF_BF_GRAY_REPLICATED = 1
+# cv::BorderTypes as rf_joint_bilateral_u8_border / rf_joint_bilateral_f32 take them (cv2.BORDER_*)
+RF_BORDER_CONSTANT, RF_BORDER_REPLICATE, RF_BORDER_REFLECT, RF_BORDER_WRAP, RF_BORDER_REFLECT_101 = 0, 1, 2, 3, 4
 RF_WHDR_PIXEL_COORDS = 1
 
 _lib = None
@@ -31,8 +33,12 @@ SIGNATURES = {
     "rf_cnn_destroy": (None, [_vp]),
     "rf_cnn_forward_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rf_joint_bilateral_u8": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _i, _u, _vp]),
+    "rf_joint_bilateral_u8_border": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _i, _u, _i, _vp]),
+    "rf_joint_bilateral_f32_workspace_bytes": (_sz, [_i, _i]),
+    "rf_joint_bilateral_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _i, _i, _vp, _sz, _vp]),
     "rf_joint_bilateral_geometry": (_i, [_d, _i, _ip, _ip]),
     "rf_joint_bilateral_max_radius": (_i, []),
+    "rf_joint_bilateral_fast_max_radius": (_i, []),
     "rf_guided_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rf_guided_u8": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
     "rf_guided_max_radius": (_i, []),

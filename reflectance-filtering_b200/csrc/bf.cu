@@ -363,9 +363,21 @@ int run(const uint8_t *joint, const uint8_t *src, uint8_t *dst, int n, int h, in
 }
 }  // namespace rf
 
+namespace rf {
+namespace bfg {  // bf_generic.cu: any radius, any border type, 8-bit and CV_32F
+int run_u8(const uint8_t *joint, int jc, const uint8_t *src, int sc, uint8_t *dst, int n, int h, int w,
+           double sigma_color, double sigma_space, int d, int alpha_scale, int border, cudaStream_t st);
+int run_f32(const float *joint, int jc, const float *src, int sc, float *dst, int n, int h, int w, double sigma_color,
+            double sigma_space, int d, int border, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t workspace_f32(int n, int jc);
+extern const int MAX_RADIUS_PUBLIC;
+}
+}  // namespace rf
+
 using namespace rf;
 
-extern "C" int rf_joint_bilateral_max_radius(void) { return bf::MAX_RADIUS; }
+extern "C" int rf_joint_bilateral_max_radius(void) { return bfg::MAX_RADIUS_PUBLIC; }
+extern "C" int rf_joint_bilateral_fast_max_radius(void) { return bf::MAX_RADIUS; }
 
 extern "C" int rf_joint_bilateral_geometry(double sigma_space, int d, int *radius, int *taps)
 {
@@ -380,6 +392,37 @@ extern "C" int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t
                                      int n, int h, int w, double sigma_color, double sigma_space, int d,
                                      unsigned flags, void *stream)
 {
+    return rf_joint_bilateral_u8_border(joint, jc, src, sc, dst, n, h, w, sigma_color, sigma_space, d, flags,
+                                        RF_BORDER_REFLECT_101, stream);
+}
+
+extern "C" size_t rf_joint_bilateral_f32_workspace_bytes(int n, int jc)
+{
+    if (n < 0 || !(jc == 1 || jc == 3)) return 0;
+    return bfg::workspace_f32(n, jc);
+}
+
+extern "C" int rf_joint_bilateral_f32(const float *joint, int jc, const float *src, int sc, float *dst, int n, int h,
+                                      int w, double sigma_color, double sigma_space, int d, int border_type,
+                                      void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!joint || !src || !dst) return fail(RF_EINVAL, "rf_joint_bilateral_f32: NULL image pointer");
+    if (!(jc == 1 || jc == 3) || !(sc == 1 || sc == 3))
+        return fail(RF_EINVAL, "rf_joint_bilateral_f32: channels must be 1 or 3 (joint %d, src %d)", jc, sc);
+    if (n < 0 || h < 1 || w < 1) return fail(RF_EINVAL, "rf_joint_bilateral_f32: bad shape n=%d h=%d w=%d", n, h, w);
+    if (border_type < 0 || border_type > 4) return fail(RF_EINVAL, "rf_joint_bilateral_f32: border type %d", border_type);
+    if (n == 0) return RF_OK;
+    if (dst == joint || dst == src) return fail(RF_EINVAL, "rf_joint_bilateral_f32: dst must not alias an input");
+    if (sigma_color <= 0) sigma_color = 1;
+    if (sigma_space <= 0) sigma_space = 1;
+    return bfg::run_f32(joint, jc, src, sc, dst, n, h, w, sigma_color, sigma_space, d, border_type, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int rf_joint_bilateral_u8_border(const uint8_t *joint, int jc, const uint8_t *src, int sc, uint8_t *dst,
+                                            int n, int h, int w, double sigma_color, double sigma_space, int d,
+                                            unsigned flags, int border_type, void *stream)
+{
     if (!joint || !src || !dst) return fail(RF_EINVAL, "rf_joint_bilateral_u8: NULL image pointer");
     if (!(jc == 1 || jc == 3) || !(sc == 1 || sc == 3))
         return fail(RF_EINVAL, "rf_joint_bilateral_u8: channels must be 1 or 3 (joint %d, src %d)", jc, sc);
@@ -392,11 +435,19 @@ extern "C" int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t
         return fail(RF_EINVAL, "rf_joint_bilateral_u8: RF_BF_GRAY_REPLICATED needs 1-channel planes");
     if (sigma_color <= 0) sigma_color = 1;
     if (sigma_space <= 0) sigma_space = 1;
+    if (border_type < 0 || border_type > 4) return fail(RF_EINVAL, "rf_joint_bilateral_u8: border type %d", border_type);
+    cudaStream_t st0 = (cudaStream_t)stream;
+    const int alpha_scale = gray_rep ? 3 : 1;
+    // the tiled kernels hold the REFLECT_101 window of a tile in shared memory: other borders, radii beyond
+    // rf_joint_bilateral_fast_max_radius() (or beyond what fits for this channel combination) and batches beyond the
+    // grid limit go through the generic kernel (bf_generic.cu), which is bit-equal to the CPU restatement
+    {
+        int r0 = d <= 0 ? (int)std::nearbyint(sigma_space * 1.5) : d / 2;
+        r0 = r0 < 1 ? 1 : r0;
+        if (border_type != RF_BORDER_REFLECT_101 || r0 > bf::MAX_RADIUS || n > 65535)
+            return bfg::run_u8(joint, jc, src, sc, dst, n, h, w, sigma_color, sigma_space, d, alpha_scale, border_type, st0);
+    }
     const bf::Geometry g = bf::geometry(sigma_space, d);
-    if (g.r > bf::MAX_RADIUS)
-        return fail(RF_EUNSUPPORTED, "rf_joint_bilateral_u8: radius %d exceeds the supported maximum %d", g.r,
-                    bf::MAX_RADIUS);
-    if (n > 65535) return fail(RF_EUNSUPPORTED, "rf_joint_bilateral_u8: more than 65535 images per call");
 
     bf::Args a;
     a.joint = joint;
@@ -416,17 +467,18 @@ extern "C" int rf_joint_bilateral_u8(const uint8_t *joint, int jc, const uint8_t
     cudaStream_t st = (cudaStream_t)stream;
     const double ksq = std::sqrt(0.5 / (sigma_color * sigma_color) * 1.4426950408889634074);
     const bool gray = (jc == 1 && sc == 1);
-    if (gray)
-        return bf2::run(joint, src, dst, n, h, w, g.r, sigma_color, sigma_space, gray_rep ? 3.0 : 1.0,
-                        (cudaStream_t)stream);
+    if (gray) {
+        const int rc = bf2::run(joint, src, dst, n, h, w, g.r, sigma_color, sigma_space, gray_rep ? 3.0 : 1.0,
+                                (cudaStream_t)stream);
+        if (rc != RF_EUNSUPPORTED) return rc;
+        return bfg::run_u8(joint, jc, src, sc, dst, n, h, w, sigma_color, sigma_space, d, alpha_scale, border_type, st0);
+    }
     {
         a.ksqrt = (float)ksq;
         const int wy = bf::pick_wy(a, g, sep);
         const size_t smem = bf::smem_bytes(wy, g, sep);
-        if (smem > 227 * 1024)
-            return fail(RF_EUNSUPPORTED,
-                        "rf_joint_bilateral_u8: radius %d with %s needs %zu bytes of shared memory (limit 232448)", g.r,
-                        sep ? "a distinct joint image" : "joint == src", smem);
+        if (smem > 227 * 1024)  // r = 61..64 with a distinct colour joint: the two tiles do not fit
+            return bfg::run_u8(joint, jc, src, sc, dst, n, h, w, sigma_color, sigma_space, d, alpha_scale, border_type, st0);
         std::lock_guard<std::mutex> lk(bf::g_tab_mu);  // held until the kernel that reads the table is in the stream
         const int rc = bf::get_table(sigma_space, g, &a.tab);
         if (rc != RF_OK) return rc;

@@ -7,7 +7,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
        -Xcompiler -Wall -Wno-deprecated-gpu-targets -ccbin /usr/bin/g++)
 OBJS=()
 PIDS=()
-for f in misc bf bf2 cnn cnn_tc gf gf2 colorize whdr; do
+for f in misc bf bf2 bf_generic cnn cnn_tc gf gf2 colorize whdr; do
   rm -f "$f.o"
   "$NVCC" "${FLAGS[@]}" ${RF_PTXAS_V:+-Xptxas -v} -c "$f.cu" -o "$f.o" &
   PIDS+=($!)

@@ -23,8 +23,14 @@ from . import _native, device as dev, image_utils as iu
 # --------------------------------------------------------------------------
 # batched device entry points
 # --------------------------------------------------------------------------
-def _nhwc(t: torch.Tensor, name: str):
-    dev.check_u8_cuda(t, name)
+def _nhwc(t: torch.Tensor, name: str, allow_f32: bool = False):
+    if allow_f32 and isinstance(t, torch.Tensor) and t.dtype == torch.float32:
+        if not t.is_cuda:
+            raise TypeError("%s must be a CUDA tensor" % name)
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
+    else:
+        dev.check_u8_cuda(t, name)
     if t.dim() == 3:
         n, h, w = t.shape
         c = 1
@@ -37,32 +43,52 @@ def _nhwc(t: torch.Tensor, name: str):
     return n, h, w, c
 
 
+BORDER_DEFAULT = _native.RF_BORDER_REFLECT_101
+
+
 def joint_bilateral_device(joint: torch.Tensor, src: torch.Tensor, sigma_color: float,
                            sigma_space: float, d: int = -1, gray_replicated: bool = False,
-                           out: torch.Tensor | None = None) -> torch.Tensor:
-    """``cv2.ximgproc.jointBilateralFilter(joint, src, d, sigmaColor, sigmaSpace)`` for a batch.
+                           out: torch.Tensor | None = None, border_type: int = BORDER_DEFAULT) -> torch.Tensor:
+    """``cv2.ximgproc.jointBilateralFilter(joint, src, d, sigmaColor, sigmaSpace[, dst[, borderType]])`` for a batch.
 
-    ``gray_replicated``: joint and src are 1-channel planes standing for three equal channels
-    (the CNN's gray PNG as cv2.imread returns it); the result is the common channel."""
-    n, h, w, sc = _nhwc(src, "src")
-    nj, hj, wj, jc = _nhwc(joint, "joint")
+    uint8 or float32 tensors (both of the same depth, as OpenCV requires).  ``gray_replicated``: joint and src are
+    1-channel uint8 planes standing for three equal channels (the CNN's gray PNG as cv2.imread returns it); the
+    result is the common channel.  ``border_type``: ``cv2.BORDER_*`` value (default REFLECT_101)."""
+    n, h, w, sc = _nhwc(src, "src", allow_f32=True)
+    nj, hj, wj, jc = _nhwc(joint, "joint", allow_f32=True)
     if (nj, hj, wj) != (n, h, w):
         raise ValueError("joint and src must have the same batch and spatial size, got %r and %r"
                          % (tuple(joint.shape), tuple(src.shape)))
     if joint.device != src.device:
         raise ValueError("joint and src live on different devices")
+    if joint.dtype != src.dtype:
+        raise TypeError("joint and src must have the same depth (uint8 or float32), got %s and %s"
+                        % (joint.dtype, src.dtype))
+    if border_type not in (0, 1, 2, 3, 4):
+        raise ValueError("border_type must be one of cv2.BORDER_CONSTANT/REPLICATE/REFLECT/WRAP/REFLECT_101")
     if out is None:
         out = torch.empty_like(src)
     else:
-        dev.check_u8_cuda(out, "out")
+        if out.dtype != src.dtype or not out.is_cuda or not out.is_contiguous() or out.device != src.device:
+            raise ValueError("out must be a contiguous CUDA tensor of the depth and device of src")
         if out.shape != src.shape:
             raise ValueError("out must have the shape of src")
-    flags = _native.RF_BF_GRAY_REPLICATED if gray_replicated else 0
+    L = _native.lib()
     with torch.cuda.device(src.device):
         dev.bind_device(src.device)
-        _native.check(_native.lib().rf_joint_bilateral_u8(
-            dev.ptr(joint), jc, dev.ptr(src), sc, dev.ptr(out), n, h, w,
-            float(sigma_color), float(sigma_space), int(d), flags, dev.stream_ptr()))
+        if src.dtype == torch.float32:
+            if gray_replicated:
+                raise ValueError("gray_replicated applies to uint8 planes only")
+            need = int(L.rf_joint_bilateral_f32_workspace_bytes(n, jc))
+            ws = _workspace(src.device, max(need, 16))
+            _native.check(L.rf_joint_bilateral_f32(
+                dev.ptr(joint), jc, dev.ptr(src), sc, dev.ptr(out), n, h, w, float(sigma_color), float(sigma_space),
+                int(d), int(border_type), dev.ptr(ws), ws.numel(), dev.stream_ptr()))
+        else:
+            flags = _native.RF_BF_GRAY_REPLICATED if gray_replicated else 0
+            _native.check(L.rf_joint_bilateral_u8_border(
+                dev.ptr(joint), jc, dev.ptr(src), sc, dev.ptr(out), n, h, w,
+                float(sigma_color), float(sigma_space), int(d), flags, int(border_type), dev.stream_ptr()))
     return out
 
 
@@ -186,10 +212,9 @@ def apply_filter_device(filter_type, image: torch.Tensor, joint: torch.Tensor, s
 def _as_image(a, name):
     if not isinstance(a, np.ndarray):
         raise TypeError("%s must be a numpy array" % name)
-    if a.dtype != np.uint8:
-        # cv2.imread only ever produces uint8 on this path; ximgproc's CV_32F branch
-        # is not reachable from the reference CLI and is not implemented
-        raise TypeError("%s must be uint8 (got %s)" % (name, a.dtype))
+    if a.dtype not in (np.uint8, np.float32):
+        # OpenCV's depths for these two filters; cv2.imread only ever produces uint8 on the reference's path
+        raise TypeError("%s must be uint8 or float32 (got %s)" % (name, a.dtype))
     if a.ndim == 2:
         a = a[:, :, None]
     if a.ndim != 3 or a.shape[2] not in (1, 3):
@@ -213,6 +238,18 @@ def apply_filter(filter_type, image, joint, sigma_color, sigma_spatial):
     if img.shape[:2] != jnt.shape[:2]:
         raise ValueError("image and joint must have the same height and width, got %r and %r"
                          % (img.shape[:2], jnt.shape[:2]))
+    if img.dtype != jnt.dtype:
+        raise TypeError("image and joint must have the same depth, got %s and %s" % (img.dtype, jnt.dtype))
+    if img.dtype == np.float32:
+        # CV_32F (not reachable from the reference CLI): jointBilateralFilter_32f; the guided filter's float depth
+        # is not built
+        if filter_type != 'bilateral':
+            raise TypeError("guided filtering of float32 images is not supported (uint8 only)")
+        d = dev.bind_device()
+        tj = torch.from_numpy(np.ascontiguousarray(jnt)).to(d)[None]
+        ti = tj if joint is image else torch.from_numpy(np.ascontiguousarray(img)).to(d)[None]
+        out = joint_bilateral_device(tj, ti, sigma_color, sigma_spatial, d=-1)[0].cpu().numpy()
+        return out[:, :, 0] if squeeze else out
     d = dev.bind_device()
     same = joint is image
     timg = dev.to_device(img, "flt_img")[None]

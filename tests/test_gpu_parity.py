@@ -215,9 +215,67 @@ def test_bf_batch_equals_per_image_and_radius_limit():
     batch = filters.joint_bilateral_device(d, d, 15, 28).cpu().numpy()
     for i in range(3):
         assert np.array_equal(batch[i], filters.apply_filter("bilateral", imgs[i], imgs[i], 15, 28))
+
+
+@pytest.mark.parametrize("jc,sc,r,gray_rep", [(3, 3, 70, False), (1, 1, 100, True), (3, 1, 64, False), (1, 3, 66, False)])
+def test_bf_large_radius_runs_on_the_generic_kernel(jc, sc, r, gray_rep):
+    """Radii beyond the shared-memory-tiled kernels (rf_joint_bilateral_fast_max_radius(), and r = 61..64 with a
+    distinct colour joint) no longer fail: the generic kernel takes them, bit-equal to the oracle."""
     from reflectance_filtering_b200 import _native
+    assert _native.lib().rf_joint_bilateral_fast_max_radius() == 64 and _native.lib().rf_joint_bilateral_max_radius() >= 1024
+    joint, src = synth.natural(50, 60, 91), synth.stress(50, 60, 92)
+    joint = joint if jc == 3 else np.ascontiguousarray(joint[:, :, 1])
+    src = src if sc == 3 else np.ascontiguousarray(src[:, :, 2])
+    if gray_rep:
+        src = joint
+    out = filters.joint_bilateral_device(dev_u8(joint[None]), dev_u8(src[None]), 20.0, 10.0, d=2 * r + 1,
+                                         gray_replicated=gray_rep).cpu().numpy()[0]
+    if gray_rep:
+        j3 = np.repeat(joint[:, :, None], 3, axis=2)
+        ref = oracle.joint_bilateral(j3, j3, 2 * r + 1, 20.0, 10.0)[:, :, 0]
+    else:
+        ref = oracle.joint_bilateral(joint, src, 2 * r + 1, 20.0, 10.0)
+    assert np.array_equal(out, ref.reshape(out.shape))
     with pytest.raises(_native.NativeError, match="radius"):
-        filters.joint_bilateral_device(d, d, 20, 200.0)
+        filters.joint_bilateral_device(dev_u8(joint[None]), dev_u8(src[None]), 20, 2000.0)
+
+
+@pytest.mark.parametrize("border", [0, 1, 2, 3, 4])
+def test_bf_border_types(border):
+    joint, src = synth.natural(33, 47, 93), synth.stress(33, 47, 94)
+    for (j, s_) in ((joint, src), (np.ascontiguousarray(joint[:, :, 0]), np.ascontiguousarray(src[:, :, 0]))):
+        out = filters.joint_bilateral_device(dev_u8(j[None]), dev_u8(s_[None]), 20.0, 6.0, border_type=border).cpu().numpy()[0]
+        ref = oracle.joint_bilateral(j, s_, -1, 20.0, 6.0, border_type=border)
+        if border == 4:    # the tiled kernels: +-1 LSB of rounding ties
+            mx, frac = lsb_stats(out, ref.reshape(out.shape))
+            assert mx <= 1 and frac < 2e-3
+        else:              # the generic kernel repeats the oracle's arithmetic
+            assert np.array_equal(out, ref.reshape(out.shape)), border
+
+
+@pytest.mark.parametrize("jc,sc,border", [(3, 3, 4), (1, 1, 4), (3, 1, 1), (1, 3, 0), (3, 3, 3)])
+def test_bf_float32_images(jc, sc, border):
+    """CV_32F joint / src (jointBilateralFilter_32f) through rf_joint_bilateral_f32 and the numpy operator."""
+    rng = np.random.default_rng(95)
+    n = 2
+    joint = (rng.random((n, 40, 52, 3)) * 255).astype(np.float32)
+    src = (rng.random((n, 40, 52, 3)) * 300 - 50).astype(np.float32)
+    joint = joint if jc == 3 else np.ascontiguousarray(joint[..., 0])
+    src = src if sc == 3 else np.ascontiguousarray(src[..., 1])
+    out = filters.joint_bilateral_device(torch.from_numpy(joint).cuda(), torch.from_numpy(src).cuda(), 30.0, 4.0,
+                                         border_type=border).cpu().numpy()
+    for i in range(n):   # the exp table is scaled to each image's own range
+        ref = oracle.joint_bilateral(joint[i], src[i], -1, 30.0, 4.0, border_type=border)
+        assert np.abs(out[i] - ref.reshape(out[i].shape)).max() <= 1e-3, i     # values up to 250: a few ulp
+    if border == 4:
+        got = filters.apply_filter("bilateral", src[0], joint[0], 30.0, 4.0)
+        assert got.dtype == np.float32 and np.abs(got - out[0].reshape(got.shape)).max() == 0
+        self_guided = filters.apply_filter("bilateral", joint[0], joint[0], 30.0, 4.0)
+        import cv2
+        want = cv2.bilateralFilter(joint[0], -1, 30.0, 4.0)
+        assert np.abs(self_guided - want).max() <= 2e-6 * 255 * 2
+    with pytest.raises(TypeError):
+        filters.apply_filter("bilateral", src[0], joint[0].astype(np.uint8), 30.0, 4.0)
 
 
 # ---- guided filter -----------------------------------------------------------------------------

@@ -118,6 +118,54 @@ def test_joint_bilateral_distinct_joint_matches_numpy_restatement(jc, sc, scol, 
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("border", [0, 1, 2, 4])
+def test_joint_bilateral_border_types_bit_exact_vs_cv2(border):
+    """borderType argument: cv2.bilateralFilter takes the same argument, so joint == src pins every type it
+    accepts (it rejects BORDER_WRAP, which is checked against the numpy restatement below)."""
+    import cv2
+    img = synth.natural(41, 37, 81)
+    for im in (img, np.ascontiguousarray(img[:, :, 1])):
+        want = cv2.bilateralFilter(im, -1, 20.0, 5.0, borderType=border)
+        assert np.array_equal(oracle.joint_bilateral(im.copy(), im, -1, 20.0, 5.0, border_type=border), want)
+
+
+@pytest.mark.parametrize("border", [0, 1, 2, 3, 4])
+def test_joint_bilateral_border_types_distinct_joint(border):
+    joint, src = synth.natural(23, 31, 82), synth.stress(23, 31, 83)
+    a = oracle.joint_bilateral(joint, src, -1, 20.0, 8.0, border_type=border)     # radius 12 > half the height
+    assert np.array_equal(a, anchors.joint_bilateral_numpy(joint, src, -1, 20.0, 8.0, border_type=border))
+
+
+@pytest.mark.parametrize("cn,sc,ss,scale", [(3, 20.0, 4.0, 255.0), (1, 0.1, 3.0, 1.0), (3, 0.05, 2.0, 1.0)])
+def test_joint_bilateral_f32_pinned_vs_cv2(cn, sc, ss, scale):
+    """CV_32F (SURVEY A.2 last bullet, 8f-4): for joint == src the restatement must agree with cv2.bilateralFilter on
+    float32 images (imgproc's bilateralFilter_32f has the structure ximgproc's joint version copies) to float
+    rounding: summation order differs (SIMD), nothing else."""
+    import cv2
+    rng = np.random.default_rng(84)
+    img = (rng.random((35, 29, cn)) * scale).astype(np.float32)
+    img = img if cn == 3 else img[:, :, 0].copy()
+    want = cv2.bilateralFilter(img, -1, sc, ss)
+    got = oracle.joint_bilateral(img.copy(), img, -1, sc, ss)
+    assert got.dtype == np.float32 and got.shape == want.shape
+    assert np.abs(got - want).max() <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("jc,sc_,border", [(3, 3, 4), (1, 3, 1), (3, 1, 2), (1, 1, 0), (3, 3, 3)])
+def test_joint_bilateral_f32_distinct_joint_matches_numpy_restatement(jc, sc_, border):
+    rng = np.random.default_rng(85)
+    joint = (rng.random((27, 33, 3)) * 255).astype(np.float32)
+    src = (rng.random((27, 33, 3)) * 100 - 20).astype(np.float32)
+    joint = joint if jc == 3 else joint[:, :, 0].copy()
+    src = src if sc_ == 3 else src[:, :, 1].copy()
+    a = oracle.joint_bilateral(joint, src, -1, 25.0, 3.0, border_type=border)
+    b = anchors.joint_bilateral_f32_numpy(joint, src, -1, 25.0, 3.0, border_type=border)
+    assert a.shape == src.shape and np.abs(a - b).max() <= 1e-4 * 120      # float32 sums in the same order: ~1 ulp
+    flat = np.full_like(joint, 7.5)                                         # constant joint: spatial Gaussian only
+    c = oracle.joint_bilateral(flat, src, -1, 25.0, 3.0, border_type=border)
+    assert np.isfinite(c).all()
+
+
 @pytest.mark.parametrize("r", [1, 7, 45])
 def test_box_mean_bit_exact_vs_cv2(G, r):
     assert np.array_equal(oracle.box_mean_reflect(G["box_in"], r), G["box_r%d" % r])
