@@ -59,7 +59,7 @@ PARITY = {
     "cnn": "max abs error < 1e-5 vs cv2.dnn on the reference prototxt + caffemodel (tolerance 1e-3)",
     "bf": "+-1 LSB vs a restatement that is bit-equal to cv2.bilateralFilter (joint == src) on every test image",
     "gf": "unpinned vs ximgproc: +-1 LSB vs two independent in-house restatements of guided_filter.cpp and within "
-          "2 LSB of a float64 He-et-al. formulation; no cv2.ximgproc build exists offline to pin against",
+          "1 LSB of a float64 He-et-al. formulation; no cv2.ximgproc build exists offline to pin against",
 }
 
 
