@@ -242,7 +242,9 @@ def run_reference(args, rank: int):
 # captures, not from this run: every such number carries the file it was read from.
 NCU = {
     "bf_gray2": {"dram_bytes": 12633600, "source": "profiles/r01_bf_gray2_ncu_full.txt (64 x 512x384)"},
-    "gf_x3": {"dram_bytes": None, "warp_instructions": None, "source": None},   # filled from profiles/r02_gf_final_ncu_full.txt
+    # the six launches of a 3-iteration call at 64 x 512x384 (pass_a<full+stats>, pass_b, 2 x (pass_a<source only>,
+    # pass_b)) + pack: 2.23 GB read + 1.18 GB written, 500.9 M warp instructions
+    "gf_x3": {"dram_bytes": 3412000000, "warp_instructions": 500.9e6, "source": "profiles/r02_gf_final_ncu_full.txt"},
 }
 
 
