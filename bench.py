@@ -579,6 +579,8 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     roofline = {
         "kernel": "bf_gray2_kernel", "bound": "sfu", "achieved": achieved_taps / 1e9, "peak": sfu_peak / 1e9,
         "unit": "Gtap/s (1 MUFU.EX2 per tap; peak = SMs*16*sm_max_mhz)", "frac": achieved_taps / sfu_peak,
+        "note": "the roofline assumes one MUFU.EX2 per tap; the kernel evaluates one weight pair in eight with an FMA-pipe "
+                "polynomial instead, so the XU pipe itself is ~90 % busy (DESIGN.md K3)",
         "frac_at_observed_clock": (achieved_taps / (sms * 16 * f_obs)) if f_obs else None,
         "fp32_lane_ops": {"per_tap": 4, "achieved_Gop_s": achieved_taps * 4 / 1e9, "peak_Gop_s": alu_peak / 1e9,
                           "frac": achieved_taps * 4 / alu_peak},

@@ -34,7 +34,8 @@ struct Args {
     const float *tab;  // device: (r+1) x nchunk float4, then (r+1) ints (even half widths)
     int n, h, w, dc;
     int r, rpad, pitch, nchunk;
-    float ksqrt;  // sqrt(0.5 / sigma_color^2 * log2 e) * alpha_scale
+    float ksqrt;  // sqrt(0.5 / sigma_color^2 * log2 e) * alpha_scale: the joint tile is stored pre-multiplied by it
+    float inv_ksqrt;
 };
 
 __device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b)
@@ -90,8 +91,10 @@ __device__ __forceinline__ unsigned long long exp2neg_poly2(unsigned long long a
 }
 
 // POLY: every POLY-th chunk evaluates the weights of its first neighbour with exp2neg_poly2 instead of
-// MUFU.EX2 (0 = never).  The kernel is bound by the XU pipe (one EX2 per tap) while the FMA pipe is ~60 % busy;
-// moving one pair in ten over (POLY = 5) is the measured optimum.
+// MUFU.EX2 (0 = never).  The kernel is bound by the XU pipe (one EX2 per tap); every packed instruction taken out of
+// the MUFU path (round 2: the window is stored pre-multiplied by ksqrt, which removes the FMUL2 of a tap pair) leaves
+// FMA-pipe and issue room to move more weight pairs over: one pair in eight (POLY = 4) is the measured optimum,
+// 98.7 % of the 1-MUFU-per-tap roofline.
 template <int WY, bool SEP, int POLY>
 __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
 {
@@ -117,8 +120,11 @@ __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
             const uint8_t *srow = S + (size_t)gy * a.w;
             for (int cc = lane; cc < cols; cc += 32) {
                 const int gx = reflect101(tx0 - a.rpad + cc, a.w);
-                tj[yy * a.pitch + cc] = (float)jrow[gx];
-                if (SEP) ts[yy * a.pitch + cc] = (float)srow[gx];
+                // the joint window is stored as ksqrt * J: the range term of a tap is then (dJ')^2, one packed
+                // instruction less per tap pair.  With joint == src the sums come out scaled and are divided at the
+                // end; a distinct source is scaled the same way so that equal inputs give equal bytes on both paths
+                tj[yy * a.pitch + cc] = (float)jrow[gx] * a.ksqrt;
+                if (SEP) ts[yy * a.pitch + cc] = (float)srow[gx] * a.ksqrt;
             }
         }
         const int n4 = (a.r + 1) * a.nchunk * 4 + (a.r + 1);
@@ -132,7 +138,6 @@ __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
     const float *jc_p = tj + (ty + a.r) * a.pitch + a.rpad + x0;
     const unsigned long long jc2 = pack2(jc_p[0], jc_p[1]);
     const unsigned long long neg1 = pack2(-1.0f, -1.0f);
-    const unsigned long long ks2 = pack2(a.ksqrt, a.ksqrt);
     unsigned long long sum2 = 0ull, wsum2 = 0ull;
     const int r = a.r;
     for (int dyi = 0; dyi <= 2 * r; ++dyi) {
@@ -150,8 +155,7 @@ __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
             const float2 sn = SEP ? srow[t] : jn;
             const float4 e = trow[t];
             {   // neighbour qb: taps (p0: dx = qb, p1: dx = qb - 1)
-                const unsigned long long d2 = ffma2r(pack2(jn.x, jn.x), neg1, jc2);
-                const unsigned long long u2 = fmul2(d2, ks2);
+                const unsigned long long u2 = ffma2r(pack2(jn.x, jn.x), neg1, jc2);
                 const unsigned long long a2 = ffma2r(u2, u2, pack2(e.x, e.y));
                 unsigned long long w;
                 if (decltype(use_poly)::value) {
@@ -165,8 +169,7 @@ __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
                 wsum2 = fadd2(wsum2, w);
             }
             {   // neighbour qb + 1: taps (p0: dx = qb + 1, p1: dx = qb)
-                const unsigned long long d2 = ffma2r(pack2(jn.y, jn.y), neg1, jc2);
-                const unsigned long long u2 = fmul2(d2, ks2);
+                const unsigned long long u2 = ffma2r(pack2(jn.y, jn.y), neg1, jc2);
                 const unsigned long long a2 = ffma2r(u2, u2, pack2(e.z, e.w));
                 float a0, a1;
                 unpack2(a2, a0, a1);
@@ -198,7 +201,8 @@ __global__ void __launch_bounds__(32 * WY) bf_gray2_kernel(const Args a)
     for (int p = 0; p < 2; ++p) {
         const int gx = tx0 + x0 + p;
         if (gx >= a.w) break;
-        const uint8_t v = sat_u8(__fdiv_rn(sv[p], wv[p]));
+        const float q = __fdiv_rn(sv[p], wv[p]);
+        const uint8_t v = sat_u8(q * a.inv_ksqrt);
         uint8_t *o = drow + (size_t)gx * a.dc;
         o[0] = v;
         if (a.dc == 3) {
@@ -287,15 +291,16 @@ static size_t smem_bytes(int wy, const Geometry &g, bool sep)
     return tile * (sep ? 2 : 1) + ((size_t)(g.r + 1) * g.nchunk * 4 + (g.r + 1)) * 4;
 }
 
-// RF_BF_POLY=<n> overrides how often the polynomial path is used (0 = never); measured on B200 (64x512x384, c20 s22): off 10.27 ms, every 5th chunk 9.87 ms,
-// every 3rd 10.57 ms -- the polynomial's dependent chain and half-rate IMAD/FFMA2 cost more than the pipe model says
+// RF_BF_POLY=<n> overrides how often the polynomial path is used (0 = never, n = first neighbour of every n-th chunk).
+// Measured on B200, 64x512x384, c20 s22 (profiles/r02_bf_poly_sweep.txt): with the pre-scaled window (round 2) off
+// 10.19 ms, n = 5: 9.59, 4: 9.34, 3: 9.46, 2: 10.43; before it (round 1) off 10.33, 5: 9.87, 4: 9.99, 3: 10.57.
 static int poly_every()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("RF_BF_POLY");
-        v = e ? atoi(e) : 5;
-        if (v != 0) v = 5;
+        v = e ? atoi(e) : 4;
+        if (v != 0 && (v < 2 || v > 5)) v = 4;
     }
     return v;
 }
@@ -335,7 +340,9 @@ int run(const uint8_t *joint, const uint8_t *src, uint8_t *dst, int n, int h, in
     a.rpad = g.rpad;
     a.pitch = g.pitch;
     a.nchunk = g.nchunk;
-    a.ksqrt = (float)(std::sqrt(0.5 / (sigma_color * sigma_color) * 1.4426950408889634074) * alpha_scale);
+    const double ks = std::sqrt(0.5 / (sigma_color * sigma_color) * 1.4426950408889634074) * alpha_scale;
+    a.ksqrt = (float)ks;
+    a.inv_ksqrt = (float)(1.0 / (double)a.ksqrt);
     const bool sep = joint != src;
     // rows per CTA: big tiles amortise the window fill, small ones balance small grids over the SMs
     const long tiles16 = (long)((w + TW - 1) / TW) * ((h + 15) / 16) * n;
@@ -353,7 +360,11 @@ int run(const uint8_t *joint, const uint8_t *src, uint8_t *dst, int n, int h, in
     case WY:                                                                                  \
         switch (poly_every()) {                                                               \
             case 0: return RF_BF2P(WY, 0);                                                    \
-            default: return RF_BF2P(WY, 5);                                                   \
+            case 2: return RF_BF2P(WY, 2);                                                    \
+            case 3: return RF_BF2P(WY, 3);                                                    \
+            case 4: return RF_BF2P(WY, 4);                                                    \
+            case 5: return RF_BF2P(WY, 5);                                                    \
+            default: return RF_BF2P(WY, 4);                                                   \
         }
     switch (wy) {
         RF_BF2(4);
