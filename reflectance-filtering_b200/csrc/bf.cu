@@ -37,7 +37,7 @@ struct Args {
     const uint8_t *joint;
     const uint8_t *src;
     uint8_t *dst;
-    const float *tab;  // device: (r+1) x tabw exponents, then (r+1) ints (row widths, ceil4)
+    const float *tab;  // device: (r+1) x 2 x tabw exponents, then (r+1) ints (row half widths, ceil4), then (r+1) exact ones
     int jc, sc, dc;
     int n, h, w;
     int r, rpad, pitch, tabw;
@@ -72,7 +72,7 @@ __device__ __forceinline__ void fill_packed(uint32_t *tile, const uint8_t *img, 
 
 __device__ __forceinline__ void load_table(float *tab_s, const Args &a)
 {
-    const int n = (a.r + 1) * 2 * a.tabw + (a.r + 1);
+    const int n = (a.r + 1) * 2 * a.tabw + 2 * (a.r + 1);
     for (int i = threadIdx.x; i < n; i += blockDim.x) tab_s[i] = a.tab[i];
 }
 
@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
     for (int dyi = 0; dyi <= 2 * r; ++dyi) {
         const int ady = dyi < r ? r - dyi : dyi - r;
         const int w4 = roww4[ady];
+        const int hw = roww4[a.r + 1 + ady];  // exact half width of this row of the disc
         const uint32_t *jrow = tj + (ty + dyi) * a.pitch + a.rpad + x0;
         const uint32_t *srow = ts + (ty + dyi) * a.pitch + a.rpad + x0;
         const float *trowA = tab + ady * 2 * a.tabw + a.rpad;  // E(dx), dx = index - 7 relative to qb
@@ -142,8 +143,11 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
         // (qb = -w4) lies left of every window of outputs 4..7 and the last one (qb = P + w4 - 4) right of every
         // window of outputs 0..3 (their table entries are +inf = weight exactly 0), so those halves are skipped:
         // ~6 % fewer taps at r = 33, identical results.
-        auto quad = [&](const int qb, auto plo_c, auto phi_c) {
-            constexpr int PLO = decltype(plo_c)::value, PHI = decltype(phi_c)::value;
+        // EDGE 1 / 2 (the two quads at the left / right end of a row): a tap pair that lies outside the window of its
+        // output for every lane -- dx = qb + jp - p beyond -hw / +hw, a warp-uniform test -- is skipped (weights exactly 0):
+        // eight outputs share one neighbour range, which costs ~13 % of the taps at r = 33 without it.
+        auto quad = [&](const int qb, auto plo_c, auto phi_c, auto edge_c) {
+            constexpr int PLO = decltype(plo_c)::value, PHI = decltype(phi_c)::value, EDGE = decltype(edge_c)::value;
             const uint4 jn = *reinterpret_cast<const uint4 *>(jrow + qb);
             const uint4 sn = SEP ? *reinterpret_cast<const uint4 *>(srow + qb) : jn;
             const float4 a0 = *reinterpret_cast<const float4 *>(trowA + qb);
@@ -168,6 +172,8 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
             for (int jp = 0; jp < 4; jp += 2) {
 #pragma unroll
                 for (int p = PLO; p < PHI; ++p) {
+                    if (EDGE == 1 && qb + hw < p - jp - 1) continue;  // both taps left of output p's window
+                    if (EDGE == 2 && qb - hw > p - jp) continue;      // both taps right of it
                     uint32_t d0, d1;
                     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d0) : "r"(jc[p]), "r"(jv[jp]), "r"(0x4B000000u));
                     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d1) : "r"(jc[p]), "r"(jv[jp + 1]), "r"(0x4B000000u));
@@ -190,9 +196,19 @@ __global__ void __launch_bounds__(32 * WY) bf_color_kernel(const Args a)
         using I0 = std::integral_constant<int, 0>;
         using I4 = std::integral_constant<int, P / 2>;
         using I8 = std::integral_constant<int, P>;
-        quad(-w4, I0{}, I4{});
-        for (int qb = -w4 + 4; qb < P + w4 - 4; qb += 4) quad(qb, I0{}, I8{});
-        quad(P + w4 - 4, I4{}, I8{});
+        using E0 = std::integral_constant<int, 0>;
+        using EL = std::integral_constant<int, 1>;
+        using ER = std::integral_constant<int, 2>;
+        if (w4 >= 4) {
+            quad(-w4, I0{}, I4{}, EL{});
+            quad(-w4 + 4, I0{}, I8{}, EL{});
+            for (int qb = -w4 + 8; qb < P + w4 - 8; qb += 4) quad(qb, I0{}, I8{}, E0{});
+            quad(P + w4 - 8, I0{}, I8{}, ER{});
+            quad(P + w4 - 4, I4{}, I8{}, ER{});
+        } else {  // the one-pixel rows at the top and bottom of the disc: two quads in all
+            quad(-w4, I0{}, I4{}, E0{});
+            quad(P + w4 - 4, I4{}, I8{}, E0{});
+        }
     }
 
     const int gy = ty0 + ty;
@@ -262,7 +278,7 @@ static int get_table(double sigma_space, const Geometry &g, const float **out)
             *out = e.d_tab;
             return RF_OK;
         }
-    const int n = (g.r + 1) * 2 * g.tabw + (g.r + 1);
+    const int n = (g.r + 1) * 2 * g.tabw + 2 * (g.r + 1);
     std::vector<float> h(n);
     const double gsc = 0.5 / (sigma_space * sigma_space) * 1.4426950408889634074;
     auto E = [&](int i, int ady) -> float {
@@ -277,6 +293,7 @@ static int get_table(double sigma_space, const Geometry &g, const float **out)
         }
         const int hw = (int)std::floor(std::sqrt((double)(g.r * g.r - ady * ady)));
         reinterpret_cast<int *>(h.data())[(g.r + 1) * 2 * g.tabw + ady] = ceil4(hw);
+        reinterpret_cast<int *>(h.data())[(g.r + 1) * 2 * g.tabw + (g.r + 1) + ady] = hw;
     }
     float *d = nullptr;
     RF_CUDA_TRY(cudaMalloc(&d, n * sizeof(float)));
@@ -297,7 +314,7 @@ static int get_table(double sigma_space, const Geometry &g, const float **out)
 static size_t smem_bytes(int wy, const Geometry &g, bool sep)
 {
     const size_t tile = (size_t)rows_of(wy, g.r) * g.pitch * 4;
-    return tile * (sep ? 2 : 1) + ((size_t)(g.r + 1) * 2 * g.tabw + (g.r + 1)) * 4;
+    return tile * (sep ? 2 : 1) + ((size_t)(g.r + 1) * 2 * g.tabw + 2 * (g.r + 1)) * 4;
 }
 
 template <typename K>
