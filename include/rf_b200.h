@@ -128,6 +128,14 @@ size_t rf_guided_workspace_bytes(int sc, int n, int h, int w, int radius);
 int rf_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst, int n,
                  int h, int w, int radius, double eps, void *ws, size_t ws_bytes, void *stream);
 int rf_guided_max_radius(void);
+
+/* CV_32F guide and source (guidedFilter converts every depth to float without scaling; the result has the depth of
+ * src): float planes in, float out, no rounding.  Runs on the generic (any radius) kernels; `ws` of at least
+ * rf_guided_f32_workspace_bytes(...) bytes.  A uint8 / float mix is handled by converting the uint8 image to float
+ * first (what the Python mirror does). */
+size_t rf_guided_f32_workspace_bytes(int sc, int n, int h, int w);
+int rf_guided_f32(const float *guide, int gc, const float *src, int sc, float *dst, int n, int h, int w,
+                  int radius, double eps, void *ws, size_t ws_bytes, void *stream);
 /* The same guide applied `iterations` times: iteration k filters the uint8 output of iteration k-1
  * (createGuidedFilter(guide, radius, eps) reused for several ->filter() calls; the reference's "3 x GF"
  * setting re-runs filter_reflectance.py on its own output).  Byte-identical to `iterations` calls of

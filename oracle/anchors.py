@@ -156,8 +156,13 @@ def box_mean_cv2(plane_f32: np.ndarray, r: int) -> np.ndarray:
     return cv2.boxFilter(plane_f32, cv2.CV_32F, (k, k), normalize=True, borderType=cv2.BORDER_REFLECT)
 
 
+def _to_src_depth(q: np.ndarray, src: np.ndarray) -> np.ndarray:
+    """convertTo(depth of src): uint8 = round-half-even + saturate, float32 = as is"""
+    return q.astype(np.float32) if src.dtype == np.float32 else np.clip(np.rint(q), 0, 255).astype(np.uint8)
+
+
 def guided_cv2box(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: float) -> np.ndarray:
-    """SURVEY A.3 written on cv2.boxFilter with float32 pointwise arithmetic."""
+    """SURVEY A.3 written on cv2.boxFilter with float32 pointwise arithmetic (uint8 or float32 images)."""
     _need_cv2()
     f32 = np.float32
     eps = f32(eps)
@@ -167,14 +172,14 @@ def guided_cv2box(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: fl
         mean = lambda x: box_mean_cv2(x, radius)
         mI = mean(I)
         inv = f32(1.0) / ((mean(I * I) - mI * mI) + eps)
-        out = np.empty(src.shape, np.uint8)
+        out = np.empty(src.shape, src_u8.dtype)
         for si in range(src.shape[2]):
             p = src[:, :, si].astype(f32)
             mp = mean(p)
             al = (mean(p * I) - mp * mI) * inv
             be = mp - al * mI
             q = mean(be) + mean(al) * I
-            out[:, :, si] = np.clip(np.rint(q), 0, 255).astype(np.uint8)
+            out[:, :, si] = _to_src_depth(q, src_u8)
         return out if src_u8.ndim == 3 else out[:, :, 0]
     I = [guide_u8[:, :, c].astype(f32) for c in range(3)]
     src = src_u8 if src_u8.ndim == 3 else src_u8[:, :, None]
@@ -198,7 +203,7 @@ def guided_cv2box(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: fl
     if eps < 1e-2:
         det = np.where(np.abs(det) < 1e-6, f32(1e-6), det)
     inv = {key: v / det for key, v in cof.items()}
-    out = np.empty(src.shape, np.uint8)
+    out = np.empty(src.shape, src_u8.dtype)
     for si in range(src.shape[2]):
         p = src[:, :, si].astype(f32)
         mp = mean(p)
@@ -217,7 +222,7 @@ def guided_cv2box(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: fl
         q = mb
         for g in range(3):
             q = q + ma[g] * I[g]
-        out[:, :, si] = np.clip(np.rint(q), 0, 255).astype(np.uint8)
+        out[:, :, si] = _to_src_depth(q, src_u8)
     return out if src_u8.ndim == 3 else out[:, :, 0]
 
 
@@ -250,7 +255,7 @@ def guided_float64(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: f
         sigma = corr - mu[:, :, :, None] * mu[:, :, None, :] + eps * np.eye(gc)
     else:
         sigma = (_box_mean_f64(G[:, :, 0] ** 2, r) - mu[:, :, 0] ** 2 + eps)[:, :, None, None]
-    out = np.empty(S.shape, np.uint8)
+    out = np.empty(S.shape, src_u8.dtype)
     for c in range(S.shape[2]):
         p = S[:, :, c]
         mp = _box_mean_f64(p, r)
@@ -258,7 +263,7 @@ def guided_float64(guide_u8: np.ndarray, src_u8: np.ndarray, radius: int, eps: f
         a = np.linalg.solve(sigma, cov_ip[:, :, :, None])[:, :, :, 0]
         b = mp - (a * mu).sum(axis=2)
         q = (_box_mean_f64(a, r) * G).sum(axis=2) + _box_mean_f64(b, r)
-        out[:, :, c] = np.clip(np.rint(q), 0, 255).astype(np.uint8)
+        out[:, :, c] = _to_src_depth(q, src_u8)
     return out.reshape(src_u8.shape)
 
 

@@ -445,17 +445,30 @@ int orc_box_mean_reflect(const float *src, float *dst, int h, int w, int r)
 }
 
 /* ---- guided filter, colour (3-channel) guide, 8-bit in / 8-bit out -------- */
-static void plane_from_u8(const uint8_t *img, int c, int cn, long n, float *out)
+/* convertTo(CV_32F) of one channel, without scaling; f32 != 0: the image is CV_32F already */
+static void plane_from(const void *img, int f32, int c, int cn, long n, float *out)
 {
-    for (long i = 0; i < n; ++i) out[i] = (float)img[i * cn + c];
+    if (f32)
+        for (long i = 0; i < n; ++i) out[i] = ((const float *)img)[i * cn + c];
+    else
+        for (long i = 0; i < n; ++i) out[i] = (float)((const uint8_t *)img)[i * cn + c];
+}
+
+/* convertTo(depth of src) of the float result: uint8 rounds half-even and saturates, CV_32F is copied */
+static void store_result(const float *acc, long count, int f32, void *dst)
+{
+    if (f32)
+        memcpy(dst, acc, sizeof(float) * count);
+    else
+        for (long i = 0; i < count; ++i) ((uint8_t *)dst)[i] = sat_u8(acc[i]);
 }
 
 /* 1-channel guide (guided_filter.cpp, gCnNum == 1; SURVEY A.3 "analogous special cases", [upstream-recollection]):
  * the 1x1 "matrix" cov(I) + eps is inverted as a reciprocal, alpha = cov(I, p) * inv, beta = mean(p) - alpha * mean(I),
  * q = mean(alpha) * I + mean(beta).  Not reachable from the reference CLI (cv2.imread hands it 3 channels); part of
  * the cv2.ximgproc.guidedFilter surface behind apply_filter (filter_reflectance.py:67-70). */
-static int guided_gray_guide(const uint8_t *guide, const uint8_t *src, int sc, uint8_t *dst, int h, int w, int radius,
-                             float eps)
+static int guided_gray_guide(const void *guide, int gf32, const void *src, int sf32, int sc, void *dst, int h, int w,
+                             int radius, float eps)
 {
     const long n = (long)h * w;
     enum { NPL = 8 };
@@ -465,7 +478,7 @@ static int guided_gray_guide(const uint8_t *guide, const uint8_t *src, int sc, u
     float *I = buf, *mI = buf + n, *inv = buf + 2 * n, *tmp = buf + 3 * n, *p = buf + 4 * n, *mp = buf + 5 * n,
           *a = buf + 6 * n, *b = buf + 7 * n;
     int rc = ORC_OK;
-    plane_from_u8(guide, 0, 1, n, I);
+    plane_from(guide, gf32, 0, 1, n, I);
     rc |= orc_box_mean_reflect(I, mI, h, w, radius);
     for (long i = 0; i < n; ++i) tmp[i] = I[i] * I[i];
     rc |= orc_box_mean_reflect(tmp, inv, h, w, radius);
@@ -475,7 +488,7 @@ static int guided_gray_guide(const uint8_t *guide, const uint8_t *src, int sc, u
         inv[i] = 1.0f / v;
     }
     for (int si = 0; si < sc && rc == ORC_OK; ++si) {
-        plane_from_u8(src, si, sc, n, p);
+        plane_from(src, sf32, si, sc, n, p);
         rc |= orc_box_mean_reflect(p, mp, h, w, radius);
         for (long i = 0; i < n; ++i) tmp[i] = p[i] * I[i];
         rc |= orc_box_mean_reflect(tmp, a, h, w, radius);
@@ -489,16 +502,18 @@ static int guided_gray_guide(const uint8_t *guide, const uint8_t *src, int sc, u
         rc |= orc_box_mean_reflect(a, tmp, h, w, radius);
         for (long i = 0; i < n; ++i) acc[i * sc + si] = b[i] + tmp[i] * I[i];
     }
-    for (long i = 0; i < n * sc; ++i) dst[i] = sat_u8(acc[i]);
+    store_result(acc, n * sc, sf32, dst);
     free(buf); free(acc);
     return rc;
 }
 
-int orc_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst,
-                  int h, int w, int radius, double eps_d)
+/* guide / src: uint8 or (gf32 / sf32 != 0) CV_32F; dst has the depth of src (dDepth = -1).  The CV_32F depths are the
+ * rest of cv2.ximgproc.guidedFilter's surface, not reachable from the reference CLI. */
+int orc_guided_any(const void *guide, int gf32, int gc, const void *src, int sf32, int sc, void *dst,
+                   int h, int w, int radius, double eps_d)
 {
     if (!(gc == 1 || gc == 3) || !(sc == 1 || sc == 3) || h < 1 || w < 1 || radius < 0) return ORC_EINVAL;
-    if (gc == 1) return guided_gray_guide(guide, src, sc, dst, h, w, radius, (float)eps_d);
+    if (gc == 1) return guided_gray_guide(guide, gf32, src, sf32, sc, dst, h, w, radius, (float)eps_d);
     const long n = (long)h * w;
     const float eps = (float)eps_d;
     /* planes: I[3], mI[3], cov[6] -> inv[6], tmp, p, mp, c[3], a[3], b */
@@ -519,7 +534,7 @@ int orc_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint
     }
     int rc = ORC_OK;
     for (int i = 0; i < 3; ++i) {
-        plane_from_u8(guide, i, 3, n, I[i]);
+        plane_from(guide, gf32, i, 3, n, I[i]);
         rc |= orc_box_mean_reflect(I[i], mI[i], h, w, radius);
     }
     /* symmetric 3x3: index (k,l), k<=l -> 0:(0,0) 1:(0,1) 2:(0,2) 3:(1,1) 4:(1,2) 5:(2,2) */
@@ -553,7 +568,7 @@ int orc_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint
     }
 #undef S
     for (int si = 0; si < sc && rc == ORC_OK; ++si) {
-        plane_from_u8(src, si, sc, n, p);
+        plane_from(src, sf32, si, sc, n, p);
         rc |= orc_box_mean_reflect(p, mp, h, w, radius);
         for (int g = 0; g < 3; ++g) {
             for (long i = 0; i < n; ++i) tmp[i] = p[i] * I[g][i];
@@ -584,7 +599,13 @@ int orc_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint
             acc[i * sc + si] = v;
         }
     }
-    for (long i = 0; i < n * sc; ++i) dst[i] = sat_u8(acc[i]);
+    store_result(acc, n * sc, sf32, dst);
     free(buf); free(acc);
     return rc;
+}
+
+int orc_guided_u8(const uint8_t *guide, int gc, const uint8_t *src, int sc, uint8_t *dst,
+                  int h, int w, int radius, double eps_d)
+{
+    return orc_guided_any(guide, 0, gc, src, 0, sc, dst, h, w, radius, eps_d);
 }

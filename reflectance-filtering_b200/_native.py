@@ -42,6 +42,8 @@ SIGNATURES = {
     "rf_guided_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rf_guided_u8": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
     "rf_guided_max_radius": (_i, []),
+    "rf_guided_f32_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "rf_guided_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _d, _vp, _sz, _vp]),
     "rf_guided_iterated_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "rf_guided_iterated_u8": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _d, _i, _vp, _sz, _vp]),
     "rf_guided_row_terms": (_i, [_i, _i, _i, _i, _ip, C.POINTER(C.c_float)]),

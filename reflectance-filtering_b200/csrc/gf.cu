@@ -20,6 +20,7 @@
 // __fmul_rn/__fadd_rn forms so pass A reproduces the oracle's separate multiply/add bit for bit.
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -31,10 +32,10 @@ constexpr int NW = NT / 32;  // warps
 constexpr int MAX_RADIUS = (NT - 32) / 2;
 
 struct Args {
-    const uint8_t *guide;  // [n][h][w][3]
-    const uint8_t *src;    // [n][h][w][SC]
+    const void *guide;     // [n][h][w][GC]  uint8 or float (template parameter TI of the kernels)
+    const void *src;       // [n][h][w][SC]
     float4 *ab;            // [n][SC][h][w] (a0, a1, a2, b)
-    uint8_t *dst;          // [n][h][w][SC]
+    void *dst;             // [n][h][w][SC]  depth of src
     int n, h, w, r;
     int twa;       // output columns per strip
     int seg_rows;  // output rows per CTA
@@ -86,33 +87,43 @@ __host__ __device__ constexpr int n_quant(int sc) { return GC == 3 ? 9 + 4 * sc 
 
 // window quantities of one pixel.  Colour guide: I (3), I*I' (6), then per source channel p, p*I0, p*I1, p*I2.
 // 1-channel guide: I, I*I, then per source channel p, p*I.
-template <int SC, int GC>
+// TI = uint8_t: exact integer products.  TI = float (CV_32F images): float products, each rounded once as
+// OpenCV's multiply() of two CV_32F planes does, summed in double like its box filter.
+template <int SC, int GC, typename TI>
 struct PixA {
-    uint32_t f[n_quant<GC>(SC)];
-    __device__ __forceinline__ void load(const uint8_t *g, const uint8_t *s)
+    typedef typename std::conditional<std::is_same<TI, float>::value, float, uint32_t>::type FT;
+    FT f[n_quant<GC>(SC)];
+    __device__ __forceinline__ static FT mul(FT a, FT b)
+    {
+        if constexpr (std::is_same<TI, float>::value)
+            return __fmul_rn(a, b);
+        else
+            return a * b;
+    }
+    __device__ __forceinline__ void load(const TI *g, const TI *s)
     {
         if constexpr (GC == 3) {
-            const uint32_t i0 = g[0], i1 = g[1], i2 = g[2];
+            const FT i0 = g[0], i1 = g[1], i2 = g[2];
             f[0] = i0; f[1] = i1; f[2] = i2;
-            f[3] = i0 * i0; f[4] = i0 * i1; f[5] = i0 * i2;
-            f[6] = i1 * i1; f[7] = i1 * i2; f[8] = i2 * i2;
+            f[3] = mul(i0, i0); f[4] = mul(i0, i1); f[5] = mul(i0, i2);
+            f[6] = mul(i1, i1); f[7] = mul(i1, i2); f[8] = mul(i2, i2);
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
-                const uint32_t p = s[c];
+                const FT p = s[c];
                 f[9 + 4 * c] = p;
-                f[10 + 4 * c] = p * i0;
-                f[11 + 4 * c] = p * i1;
-                f[12 + 4 * c] = p * i2;
+                f[10 + 4 * c] = mul(p, i0);
+                f[11 + 4 * c] = mul(p, i1);
+                f[12 + 4 * c] = mul(p, i2);
             }
         } else {
-            const uint32_t i0 = g[0];
+            const FT i0 = g[0];
             f[0] = i0;
-            f[1] = i0 * i0;
+            f[1] = mul(i0, i0);
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
-                const uint32_t p = s[c];
+                const FT p = s[c];
                 f[2 + 2 * c] = p;
-                f[3 + 2 * c] = p * i0;
+                f[3 + 2 * c] = mul(p, i0);
             }
         }
     }
@@ -121,7 +132,7 @@ struct PixA {
 // ST: type of the window sums (uint32_t for r <= MAX_RADIUS_U32, where 65,025 * (2r+1)^2 < 2^32; else 64-bit)
 constexpr int MAX_RADIUS_U32 = 127;
 
-template <int SC, int GC, typename ST>
+template <int SC, int GC, typename ST, typename TI>
 __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
 {
     constexpr int Q = n_quant<GC>(SC);
@@ -139,8 +150,8 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
     const int xin = reflect(col, g.w);
     const bool is_out = tid >= r && tid < r + g.twa && col < g.w;
     const size_t img_px = (size_t)g.h * g.w;
-    const uint8_t *G = g.guide + img * img_px * GC + (size_t)xin * GC;
-    const uint8_t *S = g.src + img * img_px * SC + (size_t)xin * SC;
+    const TI *G = static_cast<const TI *>(g.guide) + img * img_px * GC + (size_t)xin * GC;
+    const TI *S = static_cast<const TI *>(g.src) + img * img_px * SC + (size_t)xin * SC;
 
     for (int q = tid; q < Q; q += NT) pref[q * (NT + 1)] = 0u;
 
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
     if (col_active) {
         for (int dy = -r; dy < r; ++dy) {
             const size_t yy = (size_t)reflect(y0 + dy, g.h);
-            PixA<SC, GC> px;
+            PixA<SC, GC, TI> px;
             px.load(G + yy * g.w * GC, S + yy * g.w * SC);
 #pragma unroll
             for (int q = 0; q < Q; ++q) V[q] += px.f[q];
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
     for (int y = y0; y < y1; ++y) {
         if (col_active) {
             const size_t yy = (size_t)reflect(y + r, g.h);
-            PixA<SC, GC> px;
+            PixA<SC, GC, TI> px;
             px.load(G + yy * g.w * GC, S + yy * g.w * SC);
 #pragma unroll
             for (int q = 0; q < Q; ++q) V[q] += px.f[q];
@@ -232,7 +243,7 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
         }
         if (col_active) {
             const size_t yy = (size_t)reflect(y - r, g.h);
-            PixA<SC, GC> px;
+            PixA<SC, GC, TI> px;
             px.load(G + yy * g.w * GC, S + yy * g.w * SC);
 #pragma unroll
             for (int q = 0; q < Q; ++q) V[q] -= px.f[q];
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(NT) gf_pass_a(const Args g)
 }
 
 // ---- pass B --------------------------------------------------------------------------------------
-template <int SC, int GC>
+template <int SC, int GC, typename TI>
 __global__ void __launch_bounds__(NT) gf_pass_b(const Args g)
 {
     constexpr int Q = 4 * SC;
@@ -285,9 +296,9 @@ __global__ void __launch_bounds__(NT) gf_pass_b(const Args g)
         for (int q = 0; q < Q; ++q) Pq[q] = V[q];
         block_scan_to_smem<double, Q>(Pq, pref, wtot);
         if (is_out) {
-            const uint8_t *gp = g.guide + (img * img_px + (size_t)y * g.w + col) * GC;
+            const TI *gp = static_cast<const TI *>(g.guide) + (img * img_px + (size_t)y * g.w + col) * GC;
             const float i0 = gp[0], i1 = GC == 3 ? gp[GC - 2] : 0.0f, i2 = GC == 3 ? gp[GC - 1] : 0.0f;
-            uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + col) * SC;
+            TI *o = static_cast<TI *>(g.dst) + (img * img_px + (size_t)y * g.w + col) * SC;
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
                 float m[4];
@@ -301,7 +312,10 @@ __global__ void __launch_bounds__(NT) gf_pass_b(const Args g)
                 v = __fadd_rn(v, __fmul_rn(m[0], i0));
                 v = __fadd_rn(v, __fmul_rn(m[1], i1));
                 v = __fadd_rn(v, __fmul_rn(m[2], i2));
-                o[c] = sat_u8(v);
+                if constexpr (std::is_same<TI, float>::value)
+                    o[c] = v;
+                else
+                    o[c] = sat_u8(v);
             }
         }
         if (col_active) add_row(reflect(y - r, g.h), -1.0);
@@ -310,10 +324,11 @@ __global__ void __launch_bounds__(NT) gf_pass_b(const Args g)
 
 static size_t per_image_ws(int sc, int h, int w) { return (size_t)sc * h * w * sizeof(float4); }
 
-template <int SC, int GC>
+template <int SC, int GC, typename TI = uint8_t>
 static int run(Args a, cudaStream_t st)
 {
-    const bool wide = a.r > MAX_RADIUS_U32;  // 64-bit window sums
+    constexpr bool F32 = std::is_same<TI, float>::value;
+    const bool wide = F32 || a.r > MAX_RADIUS_U32;  // 64-bit window sums (double for CV_32F images)
     const size_t smem_a = ((size_t)n_quant<GC>(SC) * (NT + 1 + NW)) * (wide ? sizeof(unsigned long long) : sizeof(uint32_t));
     const size_t smem_b = ((size_t)(4 * SC) * (NT + 1 + NW)) * sizeof(double);
     static DeviceOnce once;
@@ -322,9 +337,13 @@ static int run(Args a, cudaStream_t st)
     {
         std::lock_guard<std::mutex> lock(once.mu);
         if (!once.done[dev & 63]) {
-            RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC, GC, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC, GC, unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_b<SC, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            if constexpr (F32) {
+                RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC, GC, double, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            } else {
+                RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC, GC, uint32_t, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_a<SC, GC, unsigned long long, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            }
+            RF_CUDA_TRY(cudaFuncSetAttribute(gf_pass_b<SC, GC, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             once.done[dev & 63] = true;
         }
     }
@@ -342,12 +361,16 @@ static int run(Args a, cudaStream_t st)
     }
     a.seg_rows = (a.h + segs - 1) / segs;
     dim3 grid(strips, (a.h + a.seg_rows - 1) / a.seg_rows, a.n);
-    if (wide)
-        gf_pass_a<SC, GC, unsigned long long><<<grid, NT, smem_a, st>>>(a);
-    else
-        gf_pass_a<SC, GC, uint32_t><<<grid, NT, smem_a, st>>>(a);
+    if constexpr (F32) {
+        gf_pass_a<SC, GC, double, float><<<grid, NT, smem_a, st>>>(a);
+    } else {
+        if (wide)
+            gf_pass_a<SC, GC, unsigned long long, uint8_t><<<grid, NT, smem_a, st>>>(a);
+        else
+            gf_pass_a<SC, GC, uint32_t, uint8_t><<<grid, NT, smem_a, st>>>(a);
+    }
     RF_LAUNCH_CHECK("gf_pass_a");
-    gf_pass_b<SC, GC><<<grid, NT, smem_b, st>>>(a);
+    gf_pass_b<SC, GC, TI><<<grid, NT, smem_b, st>>>(a);
     RF_LAUNCH_CHECK("gf_pass_b");
     return RF_OK;
 }
@@ -483,4 +506,59 @@ extern "C" int rf_guided_iterated_u8(const uint8_t *guide, int gc, const uint8_t
 {
     return guided_impl("rf_guided_iterated_u8", guide, gc, src, sc, dst, n, h, w, radius, eps, iterations, ws, ws_bytes,
                        stream);
+}
+
+// ---- CV_32F images (the rest of cv2.ximgproc.guidedFilter's surface; not reachable from the reference CLI):
+// float guide and source (values as they are, no scaling), float result.  Generic kernels only: float products, double
+// window sums, the same solve.
+extern "C" size_t rf_guided_f32_workspace_bytes(int sc, int n, int h, int w)
+{
+    if (!(sc == 1 || sc == 3) || n < 1 || h < 1 || w < 1) return 0;
+    const size_t per = gf::per_image_ws(sc, h, w);
+    size_t want = per * (size_t)n;
+    const size_t cap = (size_t)8 << 30;
+    if (want > cap) want = (cap / per > 0 ? cap / per : 1) * per;
+    return want;
+}
+
+extern "C" int rf_guided_f32(const float *guide, int gc, const float *src, int sc, float *dst, int n, int h, int w,
+                             int radius, double eps, void *ws, size_t ws_bytes, void *stream)
+{
+    const char *fn = "rf_guided_f32";
+    if (!guide || !src || !dst || !ws) return fail(RF_EINVAL, "%s: NULL pointer", fn);
+    if (!(gc == 1 || gc == 3)) return fail(RF_EINVAL, "%s: guide channels must be 1 or 3 (got %d)", fn, gc);
+    if (!(sc == 1 || sc == 3)) return fail(RF_EINVAL, "%s: src channels must be 1 or 3 (got %d)", fn, sc);
+    if (n < 0 || h < 1 || w < 1) return fail(RF_EINVAL, "%s: bad shape n=%d h=%d w=%d", fn, n, h, w);
+    if (radius < 0) return fail(RF_EINVAL, "%s: negative radius", fn);
+    if (radius > gf::MAX_RADIUS)
+        return fail(RF_EUNSUPPORTED, "%s: radius %d exceeds the supported maximum %d", fn, radius, gf::MAX_RADIUS);
+    if (n == 0) return RF_OK;
+    if (dst == src || dst == guide) return fail(RF_EINVAL, "%s: dst must not alias an input", fn);
+    const size_t per = gf::per_image_ws(sc, h, w);
+    if (ws_bytes < per) return fail(RF_EINVAL, "%s: workspace too small (%zu < %zu bytes)", fn, ws_bytes, per);
+    if ((uintptr_t)ws % 16) return fail(RF_EINVAL, "%s: workspace must be 16-byte aligned", fn);
+    int chunk = (int)(ws_bytes / per < (size_t)n ? ws_bytes / per : (size_t)n);
+    if (chunk > 65535) chunk = 65535;
+    const size_t img_px = (size_t)h * w;
+    const int k = 2 * radius + 1;
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        gf::Args a;
+        a.n = n - i0 < chunk ? n - i0 : chunk;
+        a.guide = guide + i0 * img_px * gc;
+        a.src = src + i0 * img_px * sc;
+        a.dst = dst + i0 * img_px * sc;
+        a.ab = (float4 *)ws;
+        a.h = h;
+        a.w = w;
+        a.r = radius;
+        a.eps = (float)eps;
+        a.scale = 1.0 / ((double)k * k);
+        a.twa = 0;
+        a.seg_rows = 0;
+        cudaStream_t st = (cudaStream_t)stream;
+        const int rc = gc == 3 ? (sc == 1 ? gf::run<1, 3, float>(a, st) : gf::run<3, 3, float>(a, st))
+                               : (sc == 1 ? gf::run<1, 1, float>(a, st) : gf::run<3, 1, float>(a, st));
+        if (rc != RF_OK) return rc;
+    }
+    return RF_OK;
 }

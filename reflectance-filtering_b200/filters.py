@@ -125,13 +125,15 @@ def guided_device(guide: torch.Tensor, src: torch.Tensor, radius: int, eps: floa
     are computed once, like a reused ``createGuidedFilter`` object); byte-identical to repeated calls."""
     if iterations < 1:
         raise ValueError("iterations must be >= 1")
-    n, h, w, sc = _nhwc(src, "src")
-    ng, hg, wg, gc = _nhwc(guide, "guide")
+    n, h, w, sc = _nhwc(src, "src", allow_f32=True)
+    ng, hg, wg, gc = _nhwc(guide, "guide", allow_f32=True)
     if (ng, hg, wg) != (n, h, w):
         raise ValueError("guide and src must have the same batch and spatial size, got %r and %r"
                          % (tuple(guide.shape), tuple(src.shape)))
     if guide.device != src.device:
         raise ValueError("guide and src live on different devices")
+    if guide.dtype == torch.float32 or src.dtype == torch.float32:
+        return _guided_f32(guide, src, radius, eps, out, iterations, (n, h, w, sc, gc))
     if out is None:
         out = torch.empty_like(src)
     else:
@@ -158,6 +160,38 @@ def guided_device(guide: torch.Tensor, src: torch.Tensor, radius: int, eps: floa
                                                   int(radius), float(eps), int(iterations), dev.ptr(ws),
                                                   ws.numel() * ws.element_size(), dev.stream_ptr()))
     return out
+
+
+def _guided_f32(guide, src, radius, eps, out, iterations, dims):
+    """CV_32F guide and / or source (``rf_guided_f32``).  guidedFilter converts every depth to float without scaling
+    and returns the depth of src: a uint8 image of a mixed pair is converted here, and a uint8 source gets its result
+    rounded half-even and saturated like ``convertTo(CV_8U)``."""
+    n, h, w, sc, gc = dims
+    src_u8 = src.dtype == torch.uint8
+    g = guide if guide.dtype == torch.float32 else guide.float()
+    cur = src if not src_u8 else src.float()
+    L = _native.lib()
+    res = None
+    with torch.cuda.device(src.device):
+        dev.bind_device(src.device)
+        need = int(L.rf_guided_f32_workspace_bytes(sc, n, h, w))
+        ws = _workspace(src.device, max(need, 16))
+        for it in range(iterations):
+            last = it == iterations - 1
+            res = out if (last and out is not None and not src_u8) else torch.empty_like(cur)
+            if res.dtype != torch.float32 or not res.is_contiguous() or res.shape != cur.shape or res.device != cur.device:
+                raise ValueError("out must be a contiguous float32 CUDA tensor shaped like src")
+            _native.check(L.rf_guided_f32(dev.ptr(g), gc, dev.ptr(cur), sc, dev.ptr(res), n, h, w, int(radius),
+                                          float(eps), dev.ptr(ws), ws.numel(), dev.stream_ptr()))
+            if src_u8:   # every application returns the depth of src
+                res = torch.round(res).clamp_(0, 255)
+            cur = res
+    if src_u8:
+        res = res.to(torch.uint8)
+        if out is not None:
+            out.copy_(res)
+            return out
+    return res
 
 
 def replicate_gray_device(gray: torch.Tensor) -> torch.Tensor:
@@ -238,17 +272,19 @@ def apply_filter(filter_type, image, joint, sigma_color, sigma_spatial):
     if img.shape[:2] != jnt.shape[:2]:
         raise ValueError("image and joint must have the same height and width, got %r and %r"
                          % (img.shape[:2], jnt.shape[:2]))
-    if img.dtype != jnt.dtype:
-        raise TypeError("image and joint must have the same depth, got %s and %s" % (img.dtype, jnt.dtype))
-    if img.dtype == np.float32:
-        # CV_32F (not reachable from the reference CLI): jointBilateralFilter_32f; the guided filter's float depth
-        # is not built
-        if filter_type != 'bilateral':
-            raise TypeError("guided filtering of float32 images is not supported (uint8 only)")
+    if img.dtype == np.float32 or jnt.dtype == np.float32:
+        # CV_32F (not reachable from the reference CLI): jointBilateralFilter_32f needs both images in float (OpenCV
+        # rejects mixed depths); guidedFilter converts whatever it gets to float and returns the depth of the source
+        if filter_type == 'bilateral' and img.dtype != jnt.dtype:
+            raise TypeError("image and joint must have the same depth, got %s and %s" % (img.dtype, jnt.dtype))
         d = dev.bind_device()
         tj = torch.from_numpy(np.ascontiguousarray(jnt)).to(d)[None]
         ti = tj if joint is image else torch.from_numpy(np.ascontiguousarray(img)).to(d)[None]
-        out = joint_bilateral_device(tj, ti, sigma_color, sigma_spatial, d=-1)[0].cpu().numpy()
+        if filter_type == 'bilateral':
+            res = joint_bilateral_device(tj, ti, sigma_color, sigma_spatial, d=-1)
+        else:
+            res = guided_device(tj, ti, int(sigma_spatial), sigma_color)
+        out = res[0].cpu().numpy()
         return out[:, :, 0] if squeeze else out
     d = dev.bind_device()
     same = joint is image

@@ -350,6 +350,28 @@ def test_gf_bytes_do_not_depend_on_batch_composition():
             assert torch.equal(part, whole[lo:hi]), (iters, lo, hi)
 
 
+@pytest.mark.parametrize("gdt,sdt,sc,gc,r", [("f", "f", 3, 3, 9), ("f", "f", 1, 1, 20), ("u", "f", 1, 3, 45), ("f", "u", 3, 3, 7)])
+def test_gf_float_depths(gdt, sdt, sc, gc, r):
+    """CV_32F guide and / or source through rf_guided_f32 (device entry point and numpy operator)."""
+    rng = np.random.default_rng(96)
+    n, h, w = 2, 60, 72
+    gd = (rng.random((n, h, w, 3)) * 255).astype(np.float32 if gdt == "f" else np.uint8)
+    src = (rng.random((n, h, w, 3)) * 200).astype(np.float32 if sdt == "f" else np.uint8)
+    gd = gd if gc == 3 else np.ascontiguousarray(gd[..., 0])
+    src = src if sc == 3 else np.ascontiguousarray(src[..., 1])
+    out = filters.guided_device(torch.from_numpy(gd).cuda(), torch.from_numpy(src).cuda(), r, 3.0).cpu().numpy()
+    assert out.dtype == src.dtype and out.shape == src.shape
+    for i in range(n):
+        ref = oracle.guided(gd[i], src[i], r, 3.0)
+        if sdt == "f":
+            assert np.abs(out[i] - ref).max() <= 2e-3, (i, np.abs(out[i] - ref).max())
+        else:
+            mx, frac = lsb_stats(out[i], ref)
+            assert mx <= 1 and frac < 2e-3
+    got = filters.apply_filter("guided", src[0], gd[0], 3.0, float(r) + 0.5)
+    assert got.dtype == src.dtype and np.array_equal(got, out[0].reshape(got.shape))
+
+
 def test_gf_iterated_equals_repeated_calls():
     """rf_guided_iterated_u8 (guide statistics cached, output fed back through the packed planes) must be
     byte-identical to calling rf_guided_u8 on its own output -- fast path, generic path, gray and colour."""

@@ -220,6 +220,24 @@ def test_guided_bounded_by_float64_paper_formulation(h, w, r, eps, sc, gc):
     assert (d > 0).mean() < 1e-3, (d > 0).mean()                   # ... on < 1e-4 of the bytes (rounding ties)
 
 
+@pytest.mark.parametrize("gdt,sdt,sc,gc", [("f", "f", 3, 3), ("f", "f", 1, 1), ("u", "f", 1, 3), ("f", "u", 3, 3)])
+def test_guided_float_depths(gdt, sdt, sc, gc):
+    """CV_32F guide and / or source: guidedFilter converts to float without scaling; dst has src's depth."""
+    rng = np.random.default_rng(86)
+    gd = (rng.random((44, 52, 3)) * 255).astype(np.float32 if gdt == "f" else np.uint8)
+    src = (rng.random((44, 52, 3)) * 200).astype(np.float32 if sdt == "f" else np.uint8)
+    gd = gd if gc == 3 else np.ascontiguousarray(gd[:, :, 0])
+    src = src if sc == 3 else np.ascontiguousarray(src[:, :, 1])
+    a = oracle.guided(gd, src, 9, 3.0)
+    b = anchors.guided_cv2box(gd, src, 9, 3.0)
+    c = anchors.guided_float64(gd, src, 9, 3.0)
+    assert a.dtype == src.dtype and a.shape == src.shape
+    if sdt == "f":
+        assert np.abs(a - b).max() <= 1e-5 and np.abs(a.astype(np.float64) - c).max() <= 1e-3
+    else:
+        assert np.abs(a.astype(int) - b.astype(int)).max() <= 1 and np.abs(a.astype(int) - c.astype(int)).max() <= 1
+
+
 def test_guided_properties():
     gd = synth.flat(48, 40, 41)
     const = np.full((48, 40, 3), 77, np.uint8)
