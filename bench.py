@@ -658,7 +658,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per step per GPU")
-    ap.add_argument("--chunk", type=int, default=8, help="images per H2D/compute/D2H chunk in the e2e path")
+    ap.add_argument("--chunk", type=int, default=32, help="largest images-per-chunk of the e2e path (H2D / compute / D2H; the first chunks are smaller)")
     ap.add_argument("--cpu-images", type=int, default=6, help="sample size of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", "--no-gf", dest="no_extra", action="store_true",

@@ -65,7 +65,7 @@ class Pipeline(object):
 
     # ---- host buffers in, host buffers out ----------------------------------------------------
     def run_host(self, kind: str, images: torch.Tensor, out: torch.Tensor,
-                 guides: Optional[torch.Tensor] = None, chunk: int = 16, n_streams: int = 3,
+                 guides: Optional[torch.Tensor] = None, chunk: int = 32, n_streams: int = 4,
                  **params) -> None:
         """End-to-end over pinned HOST tensors: ``images`` ``uint8[N,H,W,3]`` (and ``guides``) are
         copied to the device chunk by chunk, run through ``cnn_bf`` / ``cnn_gf``, and the gray
@@ -97,8 +97,17 @@ class Pipeline(object):
         cur = torch.cuda.current_stream()
         for s in streams:
             s.wait_stream(cur)
-        for ci, lo in enumerate(range(0, n, chunk)):
-            hi = min(n, lo + chunk)
+        # the first chunks are small so that the kernels start after a short first copy (nothing overlaps the first
+        # host-to-device transfer); then full chunks
+        bounds, lo = [], 0
+        for size in (max(1, chunk // 8), max(1, chunk // 4), max(1, chunk // 2)):
+            if lo + size < n and size < chunk:
+                bounds.append((lo, lo + size))
+                lo += size
+        while lo < n:
+            bounds.append((lo, min(n, lo + chunk)))
+            lo += chunk
+        for ci, (lo, hi) in enumerate(bounds):
             m = hi - lo
             s = streams[ci % len(streams)]
             b = ctx["bufs"][ci % len(streams)]
