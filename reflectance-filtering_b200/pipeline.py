@@ -55,13 +55,15 @@ class Pipeline(object):
                                               gray_replicated=True, out=out)
 
     def cnn_gf(self, images: torch.Tensor, guides: torch.Tensor, sigma_color: float = 3.0,
-               sigma_spatial: float = 45.0, iterations: int = 3) -> torch.Tensor:
+               sigma_spatial: float = 45.0, iterations: int = 3, out: Optional[torch.Tensor] = None,
+               scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
         """GF(CNN, guide) applied ``iterations`` times with uint8 re-quantisation between
-        applications (three CLI invocations in the reference).  Returns ``uint8[N,H,W]``."""
+        applications (three CLI invocations in the reference).  Returns ``uint8[N,H,W]``.
+        ``out`` / ``scratch``: optional ``uint8[N,H,W]`` buffers for the result / the intermediate reflectance."""
         if iterations < 1:
             raise ValueError("iterations must be >= 1")
-        cur = self.reflectance_u8(images)
-        return filters.guided_device(guides, cur, int(sigma_spatial), sigma_color, iterations=iterations)
+        cur = self.reflectance_u8(images, out=scratch)
+        return filters.guided_device(guides, cur, int(sigma_spatial), sigma_color, out=out, iterations=iterations)
 
     # ---- host buffers in, host buffers out ----------------------------------------------------
     def run_host(self, kind: str, images: torch.Tensor, out: torch.Tensor,
@@ -119,7 +121,7 @@ class Pipeline(object):
                 else:
                     d_gd = b["guide"][:m]
                     d_gd.copy_(guides[lo:hi], non_blocking=True)
-                    res = self.cnn_gf(d_img, d_gd, **params)
+                    res = self.cnn_gf(d_img, d_gd, out=b["out"][:m], scratch=b["r8"][:m], **params)
                 out[lo:hi].copy_(res, non_blocking=True)
         for s in streams:
             cur.wait_stream(s)
