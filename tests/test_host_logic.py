@@ -291,3 +291,28 @@ def test_whdr_host_helpers():
     mean, count = whdr.reduce_mean(torch.tensor([0.2, 0.4], dtype=torch.float64))
     assert count == 2 and abs(mean - 0.3) < 1e-15
     assert whdr.reduce_mean(torch.zeros(0, dtype=torch.float64)) == (0.0, 0)
+
+
+def test_bench_reference_arm_emits_the_contract_line():
+    """bench.py --impl reference: exactly one JSON line on stdout with the contract's keys, the same `config` dict the
+    CUDA arm builds, and the parity statement (guided filter: unpinned vs ximgproc) that every record carries."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "parity"):
+        assert key in rec, key
+    assert rec["impl"] == "reference" and rec["gpu_launches"] == 0 and rec["value"] > 0
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
+    assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["d2h_bytes_per_step"] == 0
+    assert "unpinned vs ximgproc" in rec["parity"]["gf"]
+    sys.path.insert(0, root)
+    import bench
+    assert rec["config"] == bench.make_config(64, 1)
