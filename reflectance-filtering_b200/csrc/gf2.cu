@@ -779,6 +779,106 @@ __global__ void __launch_bounds__(32 * n_groups<SC>(), SC == 1 ? 4 : 1)
 template <int SC, int RB>
 __host__ __device__ constexpr int pass_b_warps() { return 4 * SC * RB; }
 
+// q = mean(a) . I + mean(b) for the pixel pairs first_idx, first_idx + idx_step, ... of output row y of a strip, from the
+// horizontal prefixes of the four vertical window sums (plane k at Prow + k * pstride); writes uint8 to dst and / or into
+// the packed planes (the input of the next iteration, mirrored halo columns included).
+template <int SC, bool R_ODD>
+__device__ __forceinline__ void solve_row(const Args &g, const float *Prow, int pstride, int img, int y, int sx0,
+                                          int first_idx, int idx_step)
+{
+    constexpr int NP = SC == 1 ? 1 : 2;
+    const int r = g.r;
+    const size_t plane = (size_t)g.h * g.wp;
+    const size_t img_px = (size_t)g.h * g.w;
+    const uint32_t *PK = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp;
+    const int n_out = min(g.twe_b, g.w - sx0);
+    const f2 ia2 = dup2(g.inv_area);
+    const bool w_even = (g.w & 1) == 0;
+for (int idx = first_idx; idx < n_out; idx += idx_step) {
+        const bool both = idx + 1 < n_out;
+        const int i = g.rh + idx;
+        const int x = sx0 + idx;
+        const uint2 gw = *reinterpret_cast<const uint2 *>(PK + g.rh + x);
+        const f2 i0 = b2f2(gw.x, gw.y, 0, false), i1 = b2f2(gw.x, gw.y, 1, false), i2 = b2f2(gw.x, gw.y, 2, false);
+        uint32_t res0[SC], res1[SC];
+#pragma unroll
+        for (int c = 0; c < SC; ++c) {
+            f2 m[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float *Pq = Prow + (4 * c + k) * pstride;
+                // (P[i+r] - P[i-r-1], P[i+r+1] - P[i-r]); i is even, so one of the two pairs is an aligned 64-bit load
+                f2 hi, lo;
+                if (R_ODD) {
+                    hi = pack2(Pq[i + r], Pq[i + r + 1]);
+                    lo = *reinterpret_cast<const f2 *>(Pq + i - r - 1);
+                } else {
+                    hi = *reinterpret_cast<const f2 *>(Pq + i + r);
+                    lo = pack2(Pq[i - r - 1], Pq[i - r]);
+                }
+                m[k] = mul2(sub2(hi, lo), ia2);
+            }
+            f2 v = m[3];
+            v = add2(v, mul2(m[0], i0));
+            v = add2(v, mul2(m[1], i1));
+            v = add2(v, mul2(m[2], i2));
+            float v0, v1;
+            unpack2(v, v0, v1);
+            res0[c] = sat_u8(v0);
+            res1[c] = sat_u8(v1);
+        }
+        if (g.store_dst) {
+            uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + x) * SC;
+            if (SC == 1) {
+                if (both && w_even)
+                    *reinterpret_cast<uint16_t *>(o) = (uint16_t)(res0[0] | (res1[0] << 8));
+                else {
+                    o[0] = (uint8_t)res0[0];
+                    if (both) o[1] = (uint8_t)res1[0];
+                }
+            } else {
+                if (both && w_even) {
+                    uint16_t *o2 = reinterpret_cast<uint16_t *>(o);
+                    o2[0] = (uint16_t)(res0[0] | (res0[1 % SC] << 8));
+                    o2[1] = (uint16_t)(res0[2 % SC] | (res1[0] << 8));
+                    o2[2] = (uint16_t)(res1[1 % SC] | (res1[2 % SC] << 8));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < SC; ++c) o[c] = (uint8_t)res0[c];
+                    if (both)
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) o[SC + c] = (uint8_t)res1[c];
+                }
+            }
+        }
+        if (g.store_packed) {
+            // the next iteration filters this output: put it where pack_kernel would have put it, mirrored
+            // halo columns included.  Other CTAs of this launch read only the guide bytes of these words.
+            uint32_t *row = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp + (SC == 1 ? 0 : plane);
+            const uint32_t w0 = SC == 1 ? (gw.x & 0x00FFFFFFu) | (res0[0] << 24)
+                                        : res0[0] | (res0[1 % SC] << 8) | (res0[2 % SC] << 16);
+            const uint32_t w1 = SC == 1 ? (gw.y & 0x00FFFFFFu) | (res1[0] << 24)
+                                        : res1[0] | (res1[1 % SC] << 8) | (res1[2 % SC] << 16);
+            if (both)
+                *reinterpret_cast<uint2 *>(row + g.rh + x) = make_uint2(w0, w1);
+            else
+                row[g.rh + x] = w0;
+            if (x < g.rh || x + 1 >= g.w - g.rh) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (e == 1 && !both) break;
+                    const int xe = x + e;
+                    const uint32_t wv = e == 0 ? w0 : w1;
+                    const int xl = xe < g.rh ? g.rh - 1 - xe : -1;
+                    const int xr = xe >= g.w - g.rh ? g.rh + 2 * g.w - 1 - xe : -1;
+                    if (xl >= 0) row[xl] = wv;
+                    if (xr >= 0 && xr < g.wp) row[xr] = wv;
+                }
+            }
+        }
+    }
+}
+
 // The whole issue path of pass B is warp-uniform: the warp index, the output row and the row plan are broadcast
 // values, and the loads are issued by an elected lane.  (Issued from `if (lane == 0)` the compiler wrapped every
 // cp.async.bulk.tensor in per-operand R2UR + vote loops: 60 of the 75 instructions of the term loop,
@@ -787,7 +887,7 @@ template <int SC, int C, int RB, int NS>
 __global__ void __launch_bounds__(32 * pass_b_warps<SC, RB>(), SC == 1 ? 8 / RB : 1)
     pass_b_kernel(const __grid_constant__ CUtensorMap tmap, const Args g)
 {
-    constexpr int Q = 4 * SC, NX = 32 * C, NW = Q * RB, NP = SC == 1 ? 1 : 2;
+    constexpr int Q = 4 * SC, NX = 32 * C, NW = Q * RB;
     constexpr uint32_t ROW_BYTES = NX * 4;  // one term: the warp's row chunk of one prefix plane
     extern __shared__ __align__(128) float slots[];  // [NW][NS][NX], then NW * NS mbarriers
     uint64_t *bars = reinterpret_cast<uint64_t *>(slots + NW * NS * NX);
@@ -797,8 +897,6 @@ __global__ void __launch_bounds__(32 * pass_b_warps<SC, RB>(), SC == 1 ? 8 / RB 
     const int img = blockIdx.z;
     const int sx0 = blockIdx.y * g.twe_b;
     const int y = blockIdx.x * RB + rr;
-    const size_t plane = (size_t)g.h * g.wp;
-    const size_t img_px = (size_t)g.h * g.w;
     const int r = g.r;
     float *slot0 = slots + (warp * NS) * NX;
 
@@ -886,100 +984,10 @@ __global__ void __launch_bounds__(32 * pass_b_warps<SC, RB>(), SC == 1 ? 8 / RB 
 
     // the Q warps of a row share its pixels: one pixel pair per thread and step
     const float *Prow = slots + (rr * Q * NS) * NX;  // plane k of this row: Prow + k * NS * NX
-    const uint32_t *PK = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp;
-    const int n_out = min(g.twe_b, g.w - sx0);
-    const f2 ia2 = dup2(g.inv_area);
-    const bool w_even = (g.w & 1) == 0;
-    auto solve_rows = [&](auto r_odd) {
-        constexpr bool R_ODD = decltype(r_odd)::value;
-        for (int idx = 2 * (pl * 32 + lane); idx < n_out; idx += 2 * 32 * Q) {
-            const bool both = idx + 1 < n_out;
-            const int i = g.rh + idx;
-            const int x = sx0 + idx;
-            const uint2 gw = *reinterpret_cast<const uint2 *>(PK + g.rh + x);
-            const f2 i0 = b2f2(gw.x, gw.y, 0, false), i1 = b2f2(gw.x, gw.y, 1, false), i2 = b2f2(gw.x, gw.y, 2, false);
-            uint32_t res0[SC], res1[SC];
-    #pragma unroll
-            for (int c = 0; c < SC; ++c) {
-                f2 m[4];
-    #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float *Pq = Prow + (4 * c + k) * NS * NX;
-                    // (P[i+r] - P[i-r-1], P[i+r+1] - P[i-r]); i is even, so one of the two pairs is an aligned 64-bit load
-                    f2 hi, lo;
-                    if (R_ODD) {
-                        hi = pack2(Pq[i + r], Pq[i + r + 1]);
-                        lo = *reinterpret_cast<const f2 *>(Pq + i - r - 1);
-                    } else {
-                        hi = *reinterpret_cast<const f2 *>(Pq + i + r);
-                        lo = pack2(Pq[i - r - 1], Pq[i - r]);
-                    }
-                    m[k] = mul2(sub2(hi, lo), ia2);
-                }
-                f2 v = m[3];
-                v = add2(v, mul2(m[0], i0));
-                v = add2(v, mul2(m[1], i1));
-                v = add2(v, mul2(m[2], i2));
-                float v0, v1;
-                unpack2(v, v0, v1);
-                res0[c] = sat_u8(v0);
-                res1[c] = sat_u8(v1);
-            }
-            if (g.store_dst) {
-                uint8_t *o = g.dst + (img * img_px + (size_t)y * g.w + x) * SC;
-                if (SC == 1) {
-                    if (both && w_even)
-                        *reinterpret_cast<uint16_t *>(o) = (uint16_t)(res0[0] | (res1[0] << 8));
-                    else {
-                        o[0] = (uint8_t)res0[0];
-                        if (both) o[1] = (uint8_t)res1[0];
-                    }
-                } else {
-                    if (both && w_even) {
-                        uint16_t *o2 = reinterpret_cast<uint16_t *>(o);
-                        o2[0] = (uint16_t)(res0[0] | (res0[1 % SC] << 8));
-                        o2[1] = (uint16_t)(res0[2 % SC] | (res1[0] << 8));
-                        o2[2] = (uint16_t)(res1[1 % SC] | (res1[2 % SC] << 8));
-                    } else {
-    #pragma unroll
-                        for (int c = 0; c < SC; ++c) o[c] = (uint8_t)res0[c];
-                        if (both)
-    #pragma unroll
-                            for (int c = 0; c < SC; ++c) o[SC + c] = (uint8_t)res1[c];
-                    }
-                }
-            }
-            if (g.store_packed) {
-                // the next iteration filters this output: put it where pack_kernel would have put it, mirrored
-                // halo columns included.  Other CTAs of this launch read only the guide bytes of these words.
-                uint32_t *row = g.packed + (size_t)img * NP * plane + (size_t)y * g.wp + (SC == 1 ? 0 : plane);
-                const uint32_t w0 = SC == 1 ? (gw.x & 0x00FFFFFFu) | (res0[0] << 24)
-                                            : res0[0] | (res0[1 % SC] << 8) | (res0[2 % SC] << 16);
-                const uint32_t w1 = SC == 1 ? (gw.y & 0x00FFFFFFu) | (res1[0] << 24)
-                                            : res1[0] | (res1[1 % SC] << 8) | (res1[2 % SC] << 16);
-                if (both)
-                    *reinterpret_cast<uint2 *>(row + g.rh + x) = make_uint2(w0, w1);
-                else
-                    row[g.rh + x] = w0;
-                if (x < g.rh || x + 1 >= g.w - g.rh) {
-    #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        if (e == 1 && !both) break;
-                        const int xe = x + e;
-                        const uint32_t wv = e == 0 ? w0 : w1;
-                        const int xl = xe < g.rh ? g.rh - 1 - xe : -1;
-                        const int xr = xe >= g.w - g.rh ? g.rh + 2 * g.w - 1 - xe : -1;
-                        if (xl >= 0) row[xl] = wv;
-                        if (xr >= 0 && xr < g.wp) row[xr] = wv;
-                    }
-                }
-            }
-        }
-    };
     if (r & 1)
-        solve_rows(std::true_type{});
+        solve_row<SC, true>(g, Prow, NS * NX, img, y, sx0, 2 * (pl * 32 + lane), 2 * 32 * Q);
     else
-        solve_rows(std::false_type{});
+        solve_row<SC, false>(g, Prow, NS * NX, img, y, sx0, 2 * (pl * 32 + lane), 2 * 32 * Q);
 }
 
 // ---- host -------------------------------------------------------------------------------------------
@@ -1179,7 +1187,10 @@ static int launch(Args a, const Plan &p, int iterations, cudaStream_t st)
         a.store_packed = last ? 0 : 1;
         // one output row per CTA, two slots per warp: measured best of RB in {1, 2, 4} x NS in {2, 3, 4} (89 us against
         // 106 / 138 us for 2 / 4 rows per CTA and 95 / 114 us for 3 / 4 slots at 64 x 512x384: resident CTAs hide the
-        // plan -> TMA -> scan -> solve latency chain, not deeper prefetch within one)
+        // plan -> TMA -> scan -> solve latency chain, not deeper prefetch within one.  A persistent, warp-specialised
+        // form -- one producer warp keeping a ring of prefix rows full for four consumer warps per CTA -- was built and
+        // measured in round 2: byte-identical, but 111 / 134 / 187 us with 3 / 4 / 8 ring slots (16 / 12 / 8 consumer
+        // warps per SM): the scan + solve of a row need the 36 resident warps more than the loads need a deeper ring)
         const int rc = p.CB == 12 ? launch_b<SC, 12, 1, 2>(a, p, st) : launch_b<SC, 20, 1, 2>(a, p, st);
         if (rc != RF_OK) return rc;
     }
