@@ -241,7 +241,7 @@ def run_reference(args, rank: int):
 # Per-launch DRAM traffic and executed instructions of the kernels below come from committed `ncu --set full`
 # captures, not from this run: every such number carries the file it was read from.
 NCU = {
-    "bf_gray2": {"dram_bytes": 12633600, "source": "profiles/r01_bf_gray2_ncu_full.txt (64 x 512x384)"},
+    "bf_gray2": {"dram_bytes": 12630784, "source": "profiles/r02_bf_gray2_ncu_full.txt (64 x 512x384)"},
     # the six launches of a 3-iteration call at 64 x 512x384 (pass_a<full+stats>, pass_b, 2 x (pass_a<source only>,
     # pass_b)) + pack: 2.23 GB read + 1.18 GB written, 500.9 M warp instructions
     "gf_x3": {"dram_bytes": 3412000000, "warp_instructions": 500.9e6, "source": "profiles/r02_gf_final_ncu_full.txt"},
