@@ -110,7 +110,8 @@ class ClockSampler(object):
         nv = self.nv
         try:
             self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
-            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+            if not self.mx:   # a constant of the board: asked once, the polling loop stays fast
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)))
             mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
             for name, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
                               ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
