@@ -9,7 +9,7 @@
 // per tap, 16 lanes/clk/SM) is 86 % busy, but 15.5 % of the executed taps lie outside the disc because a
 // thread's 8 outputs x 4 neighbours form a coarse block.  This version makes the block 2 x 2:
 //   * a thread owns TWO adjacent outputs, held as the halves of 64-bit registers; every FP32 step of a tap
-//     pair is one packed instruction (FFMA2 / FMUL2 / FADD2 issue at half rate but carry two taps), so the
+//     pair is one packed instruction (FFMA2 / FADD2 issue at half rate but carry two taps), so the
 //     issue slots per tap drop from 6.3 to ~4.9 and leave the XU pipe as the only limiter;
 //   * neighbours arrive two at a time (LDS.64), executed taps / useful taps = 1.035 instead of 1.18;
 //   * the per-row spatial exponents for the four taps of a chunk come from one broadcast LDS.128 of a
@@ -38,12 +38,6 @@ struct Args {
     float inv_ksqrt;
 };
 
-__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b)
 {
     unsigned long long d;

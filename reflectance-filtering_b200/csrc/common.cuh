@@ -66,13 +66,6 @@ __device__ __forceinline__ uint8_t sat_u8(float v)
     return (uint8_t)min(max(r, 0), 255);
 }
 
-__device__ __forceinline__ float ex2_approx(float x)
-{
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
 // packed two-lane FP32 FMA (sm_100 FFMA2): d = a * b + c on both halves of a 64-bit register
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi)
 {
